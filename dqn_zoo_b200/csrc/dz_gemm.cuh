@@ -1,0 +1,423 @@
+// Grouped fp32 GEMM kernels for the learner (SIMT path: exact-fp32 products, fp32 accumulate).
+//
+// Every layer of the Nature-CNN family is expressed as one of three contractions over a small
+// table of problems (one launch covers all forward passes / streams of that layer):
+//
+//   NN  C[M,N]  = A[M,K]  * B[K,N]      forward (A = activations or implicit im2col, B = weights)
+//   TN  C[K,N]  = A[M,K]^T * G[M,N]     weight gradient (reduction over the batch*spatial dim M)
+//   NT  C[M,K]  = G[M,N]  * B[K,N]^T    input gradient  (reduction over N)
+//
+// A can be (i) a dense row-major matrix, (ii) an implicit im2col view of an NHWC float tensor or
+// (iii) an implicit im2col view of uint8 observation rows addressed through a pointer table —
+// the replay gather is fused here: conv1 reads sampled transitions in place, converting
+// uint8 -> float32 / 255 on the fly (networks.py:193).  Weight layouts follow haiku: conv HWIO
+// == row-major [KH*KW*Cin, Cout], linear [in, out] (networks_test.py:44,53).
+#pragma once
+#include "dz_common.cuh"
+
+namespace dz {
+
+enum : int { A_PLAIN = 0, A_CONV_F32 = 1, A_CONV_U8 = 2 };
+
+struct GemmProblem {
+  const void* A;        // A_PLAIN/A_CONV_F32: const float*;  A_CONV_U8: const uint8_t* const* (row table)
+  const float* B;       // NN/NT: weights [K,N];  TN: G [M,N]
+  const float* B2;      // dual (noisy) second weight matrix (sigma) or nullptr
+  float* C;
+  float* C2;            // second output (NN: pre-multiply activation E for IQN; TN: sigma-weight grad)
+  int M, N, K;
+  int lda, ldb, ldc;
+  int a_mode;
+  int H, W, Cin, KW, S, OH, OW, seg;   // conv geometry: seg = KW*Cin contiguous floats per kernel row
+  const float* bias;    // NN: [N] (or [1] when bias_shared)
+  const float* bias2;   // NN dual: sigma bias [N]
+  const float* a_scale; // NN dual: eps_in[K]; NT dual: eps_in[K] (output scale);  TN: eps_in[K]
+  const float* c_scale; // NN dual: eps_out[N]; NT dual: eps_out[N]; TN: eps_out[N]
+  const float* mul;     // NN: C = relu(..) * mul[(m / mul_div) * N + n]  (IQN Hadamard with the state embedding)
+  const float* mask;    // NT: C *= (mask[m*ldc + k] > 0)   (ReLU backward)
+  float* Cb;            // TN: bias-gradient row [N] (sum over m of G) or nullptr
+  float* Cb2;           // TN: sigma-bias gradient [N] = c_scale * colsum(G)
+  int mul_div;
+  int relu;
+  int bias_shared;
+  int splits;           // split of the reduction dimension; partial s goes to C + s*split_stride (raw sums).
+                        // NN: partial mode iff splits > 1;  TN: partial mode iff split_stride > 0
+  long long split_stride;
+};
+
+constexpr int kMaxProblems = 6;
+struct GemmBatch {
+  GemmProblem p[kMaxProblems];
+  int n;
+};
+
+// ---------------------------------------------------------------------------------------------
+// A-operand addressing: element (m, k) of the (implicit) A matrix.
+// ---------------------------------------------------------------------------------------------
+struct ARow {
+  const float* f;       // base of this row at k-segment 0 (nullptr if m out of range)
+  const uint8_t* u;
+};
+
+__device__ __forceinline__ ARow a_row_base(const GemmProblem& p, int m) {
+  ARow r{nullptr, nullptr};
+  if (m >= p.M) return r;
+  if (p.a_mode == A_PLAIN) {
+    r.f = static_cast<const float*>(p.A) + (long long)m * p.lda;
+  } else {
+    int per = p.OH * p.OW;
+    int img = m / per, rem = m - img * per;
+    int oy = rem / p.OW, ox = rem - oy * p.OW;
+    long long off = ((long long)(oy * p.S) * p.W + ox * p.S) * p.Cin;
+    if (p.a_mode == A_CONV_F32)
+      r.f = static_cast<const float*>(p.A) + (long long)img * p.H * p.W * p.Cin + off;
+    else
+      r.u = static_cast<const uint8_t* const*>(p.A)[img] + off;
+  }
+  return r;
+}
+
+// Four consecutive k (k % 4 == 0) of row r: never straddles a kernel-row segment (seg % 4 == 0).
+__device__ __forceinline__ float4 a_load4(const GemmProblem& p, const ARow& r, int k) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (k >= p.K) return v;
+  if (p.a_mode == A_PLAIN) {
+    if (r.f) v = *reinterpret_cast<const float4*>(r.f + k);
+  } else {
+    int kh = k / p.seg, rem = k - kh * p.seg;
+    long long off = (long long)kh * p.W * p.Cin + rem;
+    if (p.a_mode == A_CONV_F32) {
+      if (r.f) v = *reinterpret_cast<const float4*>(r.f + off);
+    } else if (r.u) {
+      uchar4 b = *reinterpret_cast<const uchar4*>(r.u + off);
+      v.x = __fdiv_rn((float)b.x, 255.0f);   // x.astype(float32) / 255.0  (networks.py:193)
+      v.y = __fdiv_rn((float)b.y, 255.0f);
+      v.z = __fdiv_rn((float)b.z, 255.0f);
+      v.w = __fdiv_rn((float)b.w, 255.0f);
+    }
+  }
+  return v;
+}
+
+template <int TM, int TN>
+struct Acc {
+  float v[TM][TN];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) v[i][j] = 0.f;
+  }
+};
+
+// One BK-deep rank update from shared tiles As[BK][BM+PAD], Bs[BK][BN+PAD].
+template <int BM, int BN, int BK, int TM, int TN, int PAD>
+__device__ __forceinline__ void tile_fma(const float (*As)[BM + PAD], const float (*Bs)[BN + PAD], int ty, int tx,
+                                         Acc<TM, TN>& acc) {
+#pragma unroll
+  for (int k = 0; k < BK; ++k) {
+    float a[TM], b[TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i) a[i] = As[k][ty * TM + i];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) b[j] = Bs[k][tx * TN + j];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc.v[i][j] = fmaf(a[i], b[j], acc.v[i][j]);
+  }
+}
+
+constexpr int kPad = 4;
+
+// ---------------------------------------------------------------------------------------------
+// NN: C[M,N] = A[M,K] * B[K,N]  (+ dual accumulate for noisy layers, bias / ReLU / Hadamard epilogue)
+// grid = (tiles_n, tiles_m * splits, problems)
+// ---------------------------------------------------------------------------------------------
+template <int BM, int BN, int BK, int TM, int TN, bool DUAL>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_nn_kernel(const __grid_constant__ GemmBatch batch) {
+  constexpr int NT = (BM / TM) * (BN / TN);
+  const GemmProblem& p = batch.p[blockIdx.z];
+  const int tiles_m = (p.M + BM - 1) / BM;
+  const int tile_m = blockIdx.y % tiles_m, split = blockIdx.y / tiles_m;
+  const int m0 = tile_m * BM, n0 = blockIdx.x * BN;
+  if (blockIdx.y >= tiles_m * p.splits || n0 >= p.N) return;
+  const int kchunks = (p.K + BK - 1) / BK;
+  const int per = (kchunks + p.splits - 1) / p.splits;
+  const int kc0 = split * per, kc1 = min(kchunks, kc0 + per);
+
+  __shared__ __align__(16) float As[BK][BM + kPad];
+  __shared__ __align__(16) float Bs[BK][BN + kPad];
+  __shared__ __align__(16) float As2[DUAL ? BK : 1][DUAL ? BM + kPad : 1];
+  __shared__ __align__(16) float Bs2[DUAL ? BK : 1][DUAL ? BN + kPad : 1];
+
+  const int tid = threadIdx.x, tx = tid % (BN / TN), ty = tid / (BN / TN);
+  constexpr int A_VEC = BM * BK / 4, B_VEC = BK * BN / 4;
+  constexpr int A_PER = (A_VEC + NT - 1) / NT, B_PER = (B_VEC + NT - 1) / NT;
+  ARow rows[A_PER];
+#pragma unroll
+  for (int i = 0; i < A_PER; ++i) {
+    int v = tid + i * NT;
+    rows[i] = a_row_base(p, (v < A_VEC) ? m0 + v / (BK / 4) : p.M);
+  }
+  const bool vecB = (p.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0) &&
+                    (!DUAL || (reinterpret_cast<uintptr_t>(p.B2) & 15) == 0);
+  Acc<TM, TN> acc, acc2;
+  acc.clear();
+  if (DUAL) acc2.clear();
+
+  for (int kc = kc0; kc < kc1; ++kc) {
+    const int k0 = kc * BK;
+#pragma unroll
+    for (int i = 0; i < A_PER; ++i) {
+      int v = tid + i * NT;
+      if (v < A_VEC) {
+        int r = v / (BK / 4), kq = (v % (BK / 4)) * 4;
+        float4 a = a_load4(p, rows[i], k0 + kq);
+        As[kq + 0][r] = a.x; As[kq + 1][r] = a.y; As[kq + 2][r] = a.z; As[kq + 3][r] = a.w;
+        if (DUAL) {
+          float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k0 + kq < p.K) s = *reinterpret_cast<const float4*>(p.a_scale + k0 + kq);
+          As2[kq + 0][r] = a.x * s.x; As2[kq + 1][r] = a.y * s.y; As2[kq + 2][r] = a.z * s.z; As2[kq + 3][r] = a.w * s.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < B_PER; ++i) {
+      int v = tid + i * NT;
+      if (v < B_VEC) {
+        int kr = v / (BN / 4), nq = (v % (BN / 4)) * 4;
+        int k = k0 + kr, n = n0 + nq;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f), b2 = b;
+        if (k < p.K) {
+          const float* src = p.B + (long long)k * p.ldb + n;
+          if (vecB && n + 3 < p.N) {
+            b = *reinterpret_cast<const float4*>(src);
+            if (DUAL) b2 = *reinterpret_cast<const float4*>(p.B2 + (long long)k * p.ldb + n);
+          } else {
+            const float* src2 = DUAL ? p.B2 + (long long)k * p.ldb + n : nullptr;
+            if (n + 0 < p.N) { b.x = src[0]; if (DUAL) b2.x = src2[0]; }
+            if (n + 1 < p.N) { b.y = src[1]; if (DUAL) b2.y = src2[1]; }
+            if (n + 2 < p.N) { b.z = src[2]; if (DUAL) b2.z = src2[2]; }
+            if (n + 3 < p.N) { b.w = src[3]; if (DUAL) b2.w = src2[3]; }
+          }
+        }
+        *reinterpret_cast<float4*>(&Bs[kr][nq]) = b;
+        if (DUAL) *reinterpret_cast<float4*>(&Bs2[kr][nq]) = b2;
+      }
+    }
+    __syncthreads();
+    tile_fma<BM, BN, BK, TM, TN, kPad>(As, Bs, ty, tx, acc);
+    if constexpr (DUAL) tile_fma<BM, BN, BK, TM, TN, kPad>(As2, Bs2, ty, tx, acc2);
+    __syncthreads();
+  }
+
+  // epilogue
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int m = m0 + ty * TM + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int n = n0 + tx * TN + j;
+      if (n >= p.N) continue;
+      if (p.splits > 1) {
+        float* dst = p.C + (long long)split * p.split_stride;
+        dst[(long long)m * p.ldc + n] = acc.v[i][j];
+        if (DUAL) dst[(long long)p.M * p.ldc + (long long)m * p.ldc + n] = acc2.v[i][j];  // sigma partial right after
+        continue;
+      }
+      float v = acc.v[i][j];
+      if (p.bias) v += p.bias_shared ? p.bias[0] : p.bias[n];
+      if (DUAL) {
+        float s = acc2.v[i][j];
+        if (p.bias2) s += p.bias2[n];
+        v += s * p.c_scale[n];
+      }
+      if (p.relu) v = fmaxf(v, 0.f);
+      if (p.mul) {
+        if (p.C2) p.C2[(long long)m * p.ldc + n] = v;
+        v *= p.mul[(long long)(m / p.mul_div) * p.N + n];
+      }
+      p.C[(long long)m * p.ldc + n] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TN (weight gradient): C[K,N] = sum_m A[m,K]^T G[m,N].  Row K (one past the weights) accumulates
+// the bias gradient (A treated as 1).  grid = (tiles_n, tiles_k * splits, problems); splits over m.
+// ---------------------------------------------------------------------------------------------
+template <int BMK, int BN, int BR, int TM, int TN>
+__global__ void __launch_bounds__((BMK / TM) * (BN / TN)) gemm_tn_kernel(const __grid_constant__ GemmBatch batch) {
+  constexpr int NT = (BMK / TM) * (BN / TN);
+  const GemmProblem& p = batch.p[blockIdx.z];
+  const int Kext = p.K + ((p.Cb || p.Cb2) ? 1 : 0);
+  const int tiles_k = (Kext + BMK - 1) / BMK;
+  const int tile_k = blockIdx.y % tiles_k, split = blockIdx.y / tiles_k;
+  const int kk0 = tile_k * BMK, n0 = blockIdx.x * BN;
+  if (blockIdx.y >= tiles_k * p.splits || n0 >= p.N) return;
+  const int rchunks = (p.M + BR - 1) / BR;
+  const int per = (rchunks + p.splits - 1) / p.splits;
+  const int rc0 = split * per, rc1 = min(rchunks, rc0 + per);
+
+  __shared__ __align__(16) float As[BR][BMK + kPad];
+  __shared__ __align__(16) float Bs[BR][BN + kPad];
+  const int tid = threadIdx.x, tx = tid % (BN / TN), ty = tid / (BN / TN);
+  constexpr int A_VEC = BR * BMK / 4, B_VEC = BR * BN / 4;
+  const bool vecG = (p.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0);
+  Acc<TM, TN> acc;
+  acc.clear();
+
+  for (int rc = rc0; rc < rc1; ++rc) {
+    const int r0 = rc * BR;
+    for (int v = tid; v < A_VEC; v += NT) {
+      int rr = v / (BMK / 4), kq = (v % (BMK / 4)) * 4;
+      int m = r0 + rr, k = kk0 + kq;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < p.M) {
+        if (k < p.K) {
+          ARow row = a_row_base(p, m);
+          a = a_load4(p, row, k);
+        } else if (k == p.K) {
+          a.x = 1.0f;  // bias-gradient row
+        }
+      }
+      *reinterpret_cast<float4*>(&As[rr][kq]) = a;
+    }
+    for (int v = tid; v < B_VEC; v += NT) {
+      int rr = v / (BN / 4), nq = (v % (BN / 4)) * 4;
+      int m = r0 + rr, n = n0 + nq;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < p.M) {
+        const float* src = p.B + (long long)m * p.ldb + n;
+        if (vecG && n + 3 < p.N) {
+          g = *reinterpret_cast<const float4*>(src);
+        } else {
+          if (n + 0 < p.N) g.x = src[0];
+          if (n + 1 < p.N) g.y = src[1];
+          if (n + 2 < p.N) g.z = src[2];
+          if (n + 3 < p.N) g.w = src[3];
+        }
+      }
+      *reinterpret_cast<float4*>(&Bs[rr][nq]) = g;
+    }
+    __syncthreads();
+    tile_fma<BMK, BN, BR, TM, TN, kPad>(As, Bs, ty, tx, acc);
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int k = kk0 + ty * TM + i;
+    if (k >= Kext) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int n = n0 + tx * TN + j;
+      if (n >= p.N) continue;
+      float v = acc.v[i][j];
+      if (p.split_stride > 0) {  // partial mode (even with a single split): raw sums, layout [Kext][N]
+        p.C[(long long)split * p.split_stride + (long long)k * p.N + n] = v;
+        continue;
+      }
+      if (k < p.K) {
+        if (p.C) p.C[(long long)k * p.ldc + n] = v;
+        if (p.C2) p.C2[(long long)k * p.ldc + n] = v * p.a_scale[k] * p.c_scale[n];
+      } else {
+        if (p.Cb) p.Cb[n] = v;
+        if (p.Cb2) p.Cb2[n] = v * p.c_scale[n];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NT (input gradient): C[M,K] = G[M,N] * B[K,N]^T, optional dual (noisy) term and ReLU mask.
+// grid = (tiles_k, tiles_m, problems)
+// ---------------------------------------------------------------------------------------------
+template <int BM, int BNK, int BR, int TM, int TN, bool DUAL>
+__global__ void __launch_bounds__((BM / TM) * (BNK / TN)) gemm_nt_kernel(const __grid_constant__ GemmBatch batch) {
+  constexpr int NT = (BM / TM) * (BNK / TN);
+  const GemmProblem& p = batch.p[blockIdx.z];
+  const int m0 = blockIdx.y * BM, k0 = blockIdx.x * BNK;
+  if (m0 >= p.M || k0 >= p.K) return;
+  __shared__ __align__(16) float As[BR][BM + kPad];
+  __shared__ __align__(16) float Bs[BR][BNK + kPad];
+  __shared__ __align__(16) float As2[DUAL ? BR : 1][DUAL ? BM + kPad : 1];
+  __shared__ __align__(16) float Bs2[DUAL ? BR : 1][DUAL ? BNK + kPad : 1];
+  const int tid = threadIdx.x, tx = tid % (BNK / TN), ty = tid / (BNK / TN);
+  const bool vec = (p.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) && (p.lda % 4 == 0) &&
+                   (!DUAL || (reinterpret_cast<uintptr_t>(p.B2) & 15) == 0);
+  const float* G = static_cast<const float*>(p.A);
+  Acc<TM, TN> acc, acc2;
+  acc.clear();
+  if (DUAL) acc2.clear();
+  constexpr int A_VEC = BM * BR / 4, B_VEC = BNK * BR / 4;
+
+  for (int n0 = 0; n0 < p.N; n0 += BR) {
+    for (int v = tid; v < A_VEC; v += NT) {
+      int r = v / (BR / 4), nq = (v % (BR / 4)) * 4;
+      int m = m0 + r, n = n0 + nq;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < p.M) {
+        const float* src = G + (long long)m * p.lda + n;
+        if (vec && n + 3 < p.N) {
+          g = *reinterpret_cast<const float4*>(src);
+        } else {
+          if (n + 0 < p.N) g.x = src[0];
+          if (n + 1 < p.N) g.y = src[1];
+          if (n + 2 < p.N) g.z = src[2];
+          if (n + 3 < p.N) g.w = src[3];
+        }
+      }
+      As[nq + 0][r] = g.x; As[nq + 1][r] = g.y; As[nq + 2][r] = g.z; As[nq + 3][r] = g.w;
+      if (DUAL) {
+        float s0 = n + 0 < p.N ? p.c_scale[n + 0] : 0.f, s1 = n + 1 < p.N ? p.c_scale[n + 1] : 0.f;
+        float s2 = n + 2 < p.N ? p.c_scale[n + 2] : 0.f, s3 = n + 3 < p.N ? p.c_scale[n + 3] : 0.f;
+        As2[nq + 0][r] = g.x * s0; As2[nq + 1][r] = g.y * s1; As2[nq + 2][r] = g.z * s2; As2[nq + 3][r] = g.w * s3;
+      }
+    }
+    for (int v = tid; v < B_VEC; v += NT) {
+      int kr = v / (BR / 4), nq = (v % (BR / 4)) * 4;
+      int k = k0 + kr, n = n0 + nq;
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f), b2 = b;
+      if (k < p.K) {
+        const float* src = p.B + (long long)k * p.ldb + n;
+        const float* src2 = DUAL ? p.B2 + (long long)k * p.ldb + n : nullptr;
+        if (vec && n + 3 < p.N) {
+          b = *reinterpret_cast<const float4*>(src);
+          if (DUAL) b2 = *reinterpret_cast<const float4*>(src2);
+        } else {
+          if (n + 0 < p.N) { b.x = src[0]; if (DUAL) b2.x = src2[0]; }
+          if (n + 1 < p.N) { b.y = src[1]; if (DUAL) b2.y = src2[1]; }
+          if (n + 2 < p.N) { b.z = src[2]; if (DUAL) b2.z = src2[2]; }
+          if (n + 3 < p.N) { b.w = src[3]; if (DUAL) b2.w = src2[3]; }
+        }
+      }
+      Bs[nq + 0][kr] = b.x; Bs[nq + 1][kr] = b.y; Bs[nq + 2][kr] = b.z; Bs[nq + 3][kr] = b.w;
+      if (DUAL) { Bs2[nq + 0][kr] = b2.x; Bs2[nq + 1][kr] = b2.y; Bs2[nq + 2][kr] = b2.z; Bs2[nq + 3][kr] = b2.w; }
+    }
+    __syncthreads();
+    tile_fma<BM, BNK, BR, TM, TN, kPad>(As, Bs, ty, tx, acc);
+    if constexpr (DUAL) tile_fma<BM, BNK, BR, TM, TN, kPad>(As2, Bs2, ty, tx, acc2);
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int m = m0 + ty * TM + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int k = k0 + tx * TN + j;
+      if (k >= p.K) continue;
+      float v = acc.v[i][j];
+      if (DUAL) v += p.a_scale[k] * acc2.v[i][j];
+      if (p.mask && !(p.mask[(long long)m * p.ldc + k] > 0.f)) v = 0.f;
+      p.C[(long long)m * p.ldc + k] = v;
+    }
+  }
+}
+
+}  // namespace dz

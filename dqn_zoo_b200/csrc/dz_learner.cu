@@ -1,0 +1,1529 @@
+// Learner half of the hot path: the jitted `update` of every dqn_zoo agent as hand-written CUDA.
+//
+//   networks      networks.py:58-363   (Nature-CNN torso, DQN / C51 / QR / IQN / Rainbow heads)
+//   loss_fn       dqn/agent.py:85-107, double_q/agent.py:85-111, prioritized/agent.py:86-113,
+//                 c51/agent.py:87-107, qrdqn/agent.py:88-110, rainbow/agent.py:85-109, iqn/agent.py:178-214
+//   rlax 0.1.2    q_learning, double_q_learning, clip_gradient, l2_loss, categorical_l2_project,
+//                 categorical_[double_]q_learning, quantile_q_learning (restated)
+//   optax 0.1.2   adam, rmsprop(centered), clip_by_global_norm, apply_updates
+//   _learn glue   rainbow/agent.py:181-198, prioritized/agent.py:187-206
+//
+// Gradients flow only through online(s_tm1).  All forward passes of a layer are one grouped
+// launch (dz_gemm.cuh); the replay gather is fused into conv1's operand load.
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <vector>
+
+#include "dz_gemm.cuh"
+#include "dz_internal.cuh"
+
+namespace dz {
+
+// ------------------------------------------------------------------------------------------------
+// Parameter layout (canonical names; haiku layouts) — must match oracle/learner_oracle.py:param_shapes
+// ------------------------------------------------------------------------------------------------
+
+struct TensorInfo {
+  std::string name;
+  int64_t shape[4];
+  int ndim;
+  int64_t offset, count;
+};
+
+struct Dims {
+  int H, W, C;       // observation
+  int h1, w1, h2, w2, h3, w3;
+  int feat;          // h3*w3*64
+  int out;           // head outputs (family dependent)
+};
+
+static inline int conv_out(int n, int k, int s) { return (n - k) / s + 1; }
+
+static Dims make_dims(const dz_learner_config& c) {
+  Dims d;
+  d.H = c.obs_h; d.W = c.obs_w; d.C = c.obs_c;
+  d.h1 = conv_out(d.H, 8, 4); d.w1 = conv_out(d.W, 8, 4);
+  d.h2 = conv_out(d.h1, 4, 2); d.w2 = conv_out(d.w1, 4, 2);
+  d.h3 = conv_out(d.h2, 3, 1); d.w3 = conv_out(d.w2, 3, 1);
+  d.feat = d.h3 * d.w3 * 64;
+  switch (c.kind) {
+    case DZ_C51: d.out = c.num_actions * c.num_atoms; break;
+    case DZ_QRDQN: d.out = c.num_quantiles * c.num_actions; break;
+    case DZ_RAINBOW: d.out = c.num_actions * c.num_atoms; break;
+    default: d.out = c.num_actions;
+  }
+  return d;
+}
+
+struct Layout {
+  std::vector<TensorInfo> t;
+  std::map<std::string, int> index;
+  int64_t total = 0;
+  void add(const std::string& name, std::initializer_list<int64_t> shape) {
+    TensorInfo ti;
+    ti.name = name;
+    ti.ndim = (int)shape.size();
+    ti.count = 1;
+    int i = 0;
+    for (auto s : shape) { ti.shape[i++] = s; ti.count *= s; }
+    for (; i < 4; ++i) ti.shape[i] = 1;
+    ti.offset = total;
+    total += (ti.count + 3) / 4 * 4;  // keep every tensor 16-byte aligned for float4 loads
+    index[name] = (int)t.size();
+    t.push_back(ti);
+  }
+  int64_t off(const std::string& name) const { return t[index.at(name)].offset; }
+  bool has(const std::string& name) const { return index.count(name) != 0; }
+};
+
+static Layout make_layout(const dz_learner_config& c) {
+  Layout L;
+  Dims d = make_dims(c);
+  L.add("conv1/w", {8, 8, d.C, 32}); L.add("conv1/b", {32});
+  L.add("conv2/w", {4, 4, 32, 64});  L.add("conv2/b", {64});
+  L.add("conv3/w", {3, 3, 64, 64});  L.add("conv3/b", {64});
+  if (c.kind == DZ_RAINBOW) {
+    const char* streams[2] = {"adv", "val"};
+    for (int s = 0; s < 2; ++s) {
+      std::string p = streams[s];
+      int64_t n_out = s == 0 ? (int64_t)c.num_actions * c.num_atoms : c.num_atoms;
+      L.add(p + "1/mu/w", {d.feat, 512}); L.add(p + "1/mu/b", {512});
+      L.add(p + "1/sigma/w", {d.feat, 512}); L.add(p + "1/sigma/b", {512});
+      L.add(p + "2/mu/w", {512, n_out}); L.add(p + "2/sigma/w", {512, n_out}); L.add(p + "2/sigma/b", {n_out});
+    }
+    return L;
+  }
+  if (c.kind == DZ_IQN) { L.add("embed/w", {c.latent_dim, d.feat}); L.add("embed/b", {d.feat}); }
+  L.add("fc1/w", {d.feat, 512}); L.add("fc1/b", {512});
+  L.add("head/w", {512, d.out});
+  bool shared = c.kind == DZ_DOUBLE_Q || c.kind == DZ_PRIORITIZED;
+  L.add("head/b", {shared ? 1 : d.out});
+  return L;
+}
+
+struct Bump {
+  char* base;
+  int64_t used = 0;
+  template <typename T> T* take(int64_t n) {
+    int64_t bytes = (n * (int64_t)sizeof(T) + 255) / 256 * 256;
+    T* p = base ? reinterpret_cast<T*>(base + used) : nullptr;
+    used += bytes;
+    return p;
+  }
+};
+
+static int validate(const dz_learner_config& c) {
+  if (c.kind < 0 || c.kind > DZ_IQN) return fail(DZ_EINVAL, "unknown agent kind");
+  if (c.batch <= 0 || c.batch > 1024) return fail(DZ_EINVAL, "batch must be in [1,1024]");
+  if (c.obs_c != 4) return fail(DZ_EINVAL, "obs_c must be 4 (stacked frames; conv1 reads uchar4 pixels)");
+  if (c.obs_w % 4) return fail(DZ_EINVAL, "obs_w must be a multiple of 4");
+  if (c.obs_h < 36 || c.obs_w < 36) return fail(DZ_EINVAL, "observation too small for the Nature-CNN torso");
+  if (c.num_actions <= 0 || c.num_actions > 64) return fail(DZ_EINVAL, "num_actions must be in [1,64]");
+  if ((c.kind == DZ_C51 || c.kind == DZ_RAINBOW) && (c.num_atoms < 2 || c.num_atoms > 128)) return fail(DZ_EINVAL, "num_atoms must be in [2,128]");
+  if (c.kind == DZ_QRDQN && (c.num_quantiles < 1 || c.num_quantiles > 256)) return fail(DZ_EINVAL, "num_quantiles must be in [1,256]");
+  if (c.kind == DZ_IQN) {
+    if (c.latent_dim <= 0 || c.latent_dim % 16) return fail(DZ_EINVAL, "latent_dim must be a positive multiple of 16");
+    int mx = c.tau_samples_s_tm1 > c.tau_samples_s_t ? c.tau_samples_s_tm1 : c.tau_samples_s_t;
+    mx = mx > c.tau_samples_policy ? mx : c.tau_samples_policy;
+    if (c.tau_samples_s_tm1 <= 0 || c.tau_samples_s_t <= 0 || c.tau_samples_policy <= 0 || mx > 256)
+      return fail(DZ_EINVAL, "tau sample counts must be in [1,256]");
+  }
+  return DZ_OK;
+}
+
+}  // namespace dz
+
+using namespace dz;
+
+// ------------------------------------------------------------------------------------------------
+// Small kernels
+// ------------------------------------------------------------------------------------------------
+
+namespace {
+
+struct FinishNN {  // split-K partials of an NN problem -> bias / noisy combine / relu
+  const float* partial; int splits; long long stride; int M, N; int dual;
+  const float* bias; const float* bias2; const float* c_scale; int relu; int bias_shared; float* out;
+};
+struct FinishNNBatch { FinishNN f[kMaxProblems]; int n; };
+
+__global__ void __launch_bounds__(256) finish_nn_kernel(const __grid_constant__ FinishNNBatch b) {
+  const FinishNN& f = b.f[blockIdx.y];
+  long long total = (long long)f.M * f.N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int n = (int)(i % f.N);
+    float v = 0.f, s = 0.f;
+    for (int k = 0; k < f.splits; ++k) {
+      v += f.partial[k * f.stride + i];
+      if (f.dual) s += f.partial[k * f.stride + total + i];
+    }
+    if (f.bias) v += f.bias_shared ? f.bias[0] : f.bias[n];
+    if (f.dual) {
+      if (f.bias2) s += f.bias2[n];
+      v += s * f.c_scale[n];
+    }
+    if (f.relu) v = fmaxf(v, 0.f);
+    f.out[i] = v;
+  }
+}
+
+struct FinishTN {  // split partials [Kext][N] of a TN problem -> weight / bias gradients
+  const float* partial; int splits; long long stride; int K, N;
+  float* C; float* C2; float* Cb; float* Cb2; const float* a_scale; const float* c_scale;
+};
+struct FinishTNBatch { FinishTN f[kMaxProblems]; int n; };
+
+__global__ void __launch_bounds__(256) finish_tn_kernel(const __grid_constant__ FinishTNBatch b) {
+  const FinishTN& f = b.f[blockIdx.y];
+  int Kext = f.K + ((f.Cb || f.Cb2) ? 1 : 0);
+  long long total = (long long)Kext * f.N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(i / f.N), n = (int)(i % f.N);
+    float v = 0.f;
+    for (int s = 0; s < f.splits; ++s) v += f.partial[s * f.stride + i];
+    if (k < f.K) {
+      if (f.C) f.C[i] = v;
+      if (f.C2) f.C2[i] = v * f.a_scale[k] * f.c_scale[n];
+    } else {
+      if (f.Cb) f.Cb[n] = v;
+      if (f.Cb2) f.Cb2[n] = v * f.c_scale[n];
+    }
+  }
+}
+
+// col2im for the conv input gradient: dX[b,y,x,c] = sum over kernel taps of dcol, times ReLU mask.
+__global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ dcol, const float* __restrict__ act,
+                                                     float* __restrict__ dx, int nimg, int H, int W, int Cin, int KH, int KW,
+                                                     int S, int OH, int OW) {
+  long long total = (long long)nimg * H * W * Cin;
+  const int K = KH * KW * Cin;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % Cin);
+    long long t = i / Cin;
+    int x = (int)(t % W); t /= W;
+    int y = (int)(t % H);
+    int b = (int)(t / H);
+    float v = 0.f;
+    if (act[i] > 0.f) {
+      for (int kh = 0; kh < KH; ++kh) {
+        int yy = y - kh;
+        if (yy < 0 || yy % S) continue;
+        int oy = yy / S;
+        if (oy >= OH) continue;
+        for (int kw = 0; kw < KW; ++kw) {
+          int xx = x - kw;
+          if (xx < 0 || xx % S) continue;
+          int ox = xx / S;
+          if (ox >= OW) continue;
+          v += dcol[((long long)(b * OH + oy) * OW + ox) * K + (kh * KW + kw) * Cin + c];
+        }
+      }
+    }
+    dx[i] = v;
+  }
+}
+
+__global__ void add_mask_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ act,
+                                float* __restrict__ out, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = act[i] > 0.f ? a[i] + b[i] : 0.f;
+}
+
+__global__ void sum_to_scalar_kernel(const float* __restrict__ v, int n, float* out) {
+  __shared__ float s[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += v[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < (blockDim.x >> 5) ? s[threadIdx.x] : 0.f;
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) out[0] = acc;
+  }
+}
+
+// ---- IQN helpers -------------------------------------------------------------------------------
+
+// cos(pi * i * tau), i = 1..latent; the product is formed in float32 as in networks.py:277-278.
+__global__ void iqn_cos_kernel(const float* __restrict__ taus, float* __restrict__ out, long long rows, int latent) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= rows * latent) return;
+  int j = (int)(i % latent);
+  float pim = __fmul_rn((float)(j + 1), 3.14159274101257324f);
+  out[i] = cosf(__fmul_rn(pim, taus[i / latent]));
+}
+
+// dE = dHI * F * (E > 0) in place; dF[b,k] = sum_n dHI[b,n,k] * E[b,n,k]; dfeat masked by act3 > 0.
+__global__ void __launch_bounds__(256) iqn_hadamard_bwd_kernel(float* __restrict__ dHI, const float* __restrict__ E,
+                                                               const float* __restrict__ F, float* __restrict__ dfeat,
+                                                               int B, int N, int D) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)B * D) return;
+  int b = (int)(i / D), k = (int)(i % D);
+  float f = F[i], acc = 0.f;
+  for (int n = 0; n < N; ++n) {
+    long long j = ((long long)b * N + n) * D + k;
+    float g = dHI[j], e = E[j];
+    acc += g * e;
+    dHI[j] = e > 0.f ? g * f : 0.f;
+  }
+  dfeat[i] = f > 0.f ? acc : 0.f;  // F is the post-ReLU conv3 output: mask for the conv3 pre-activation
+}
+
+// ---- randomness --------------------------------------------------------------------------------
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// kind 0: U[0,1) (IQN taus); kind 1: sign(n)*sqrt|n|, n ~ TruncNormal(-2,2) (networks.py:142-144).
+__global__ void randomness_kernel(float* __restrict__ out, long long n, uint64_t seed, const int64_t* counters, int kind,
+                                  uint32_t stream_id) {
+  long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i4 * 4 >= n) return;
+  uint64_t ctr = (uint64_t)counters[1];
+  uint32_t r[4];
+  philox4x32_10((uint32_t)i4, (uint32_t)(i4 >> 32), (uint32_t)ctr, (uint32_t)(ctr >> 32) ^ (stream_id << 24), (uint32_t)seed,
+                (uint32_t)(seed >> 32), r);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    long long i = i4 * 4 + j;
+    if (i >= n) break;
+    float u = (float)(r[j] >> 8) * (1.0f / 16777216.0f);  // [0,1)
+    if (kind == 0) {
+      out[i] = u;
+    } else {
+      const float lo = -0.95449973610364158f;  // erf(-2/sqrt(2))
+      float v = lo + (-2.0f * lo) * ((float)(r[j] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+      float x = 1.41421356237f * erfinvf(v);
+      x = fminf(fmaxf(x, -2.0f), 2.0f);
+      out[i] = copysignf(sqrtf(fabsf(x)), x);
+    }
+  }
+}
+
+__global__ void bump_counter_kernel(int64_t* counters, int which) { counters[which] += 1; }
+
+// ---- losses ------------------------------------------------------------------------------------
+
+struct LossArgs {
+  int kind, B, A, atoms, N, Ksel, Nt;  // N: #src quantiles (s_tm1), Ksel: selector samples, Nt: target samples
+  const float* out0; const float* out1; const float* out2;       // head outputs of pass 0 / 1 / 2 (see learner)
+  const float* adv0; const float* val0; const float* adv1; const float* val1; const float* adv2; const float* val2;  // rainbow
+  const int32_t* a; const float* r; const float* disc; const float* w; const float* taus0;
+  float vmax, bound, kappa;
+  float* dout; float* dadv; float* dval;      // gradients wrt pass-0 head outputs
+  float* per_example; float* priorities; float* loss_terms;  // loss_terms[b] = w_b * loss_b
+};
+
+__device__ __forceinline__ float block_sum(float v, float* smem) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = threadIdx.x < (blockDim.x >> 5) ? smem[threadIdx.x] : 0.f;
+  if (threadIdx.x < 32) t = warp_sum(t);
+  if (threadIdx.x == 0) smem[0] = t;
+  __syncthreads();
+  t = smem[0];
+  __syncthreads();
+  return t;
+}
+__device__ __forceinline__ float block_max(float v, float* smem) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = threadIdx.x < (blockDim.x >> 5) ? smem[threadIdx.x] : -INFINITY;
+  if (threadIdx.x < 32) t = warp_max(t);
+  if (threadIdx.x == 0) smem[0] = t;
+  __syncthreads();
+  t = smem[0];
+  __syncthreads();
+  return t;
+}
+
+// dqn / double_q / prioritized: rlax.q_learning / double_q_learning, clip_gradient, l2_loss.
+__global__ void __launch_bounds__(64) loss_q_kernel(LossArgs L) {
+  int b = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  const float* q_tm1 = L.out0 + (long long)b * L.A;
+  const float* q_sel = (L.kind == DZ_DQN ? L.out2 : L.out1) + (long long)b * L.A;
+  const float* q_tgt = L.out2 + (long long)b * L.A;
+  int best = 0;
+  for (int a = 1; a < L.A; ++a)
+    if (q_sel[a] > q_sel[best]) best = a;
+  int at = L.a[b];
+  float target = L.r[b] + L.disc[b] * q_tgt[best];
+  float td = target - q_tm1[at];
+  float w = L.w ? L.w[b] : 1.0f;
+  float g = fminf(fmaxf(w * td / (float)L.B, -L.bound), L.bound);  // cotangent reaching clip_gradient
+  for (int a = 0; a < L.A; ++a) L.dout[(long long)b * L.A + a] = (a == at) ? -g : 0.f;
+  L.per_example[b] = td;
+  if (L.priorities) L.priorities[b] = fabsf(td);                   // prioritized/agent.py:201
+  L.loss_terms[b] = w * 0.5f * td * td;
+}
+
+// c51 / rainbow: categorical_[double_]q_learning with categorical_l2_project + cross entropy.
+__global__ void __launch_bounds__(128) loss_categorical_kernel(LossArgs L) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x, K = L.atoms, A = L.A, tid = threadIdx.x;
+  float* red = sm;             // [32]
+  float* logit = sm + 32;      // [K] scratch logits
+  float* p_tgt = logit + K;    // [K]
+  float* proj = p_tgt + K;     // [K]
+  float* qsel = proj + K;      // [A]
+  float* colmean = qsel + A;   // [K] rainbow mean over actions of adv
+  const bool rb = L.kind == DZ_RAINBOW;
+  const float dz_ = 2.0f * L.vmax / (float)(K - 1);
+  auto support = [&](int i) { return (float)((double)(-L.vmax) + (double)i * (2.0 * (double)L.vmax / (double)(K - 1))); };
+
+  // logits of (pass, action) into `logit` (rainbow: dueling combine, networks.py:251)
+  auto load_logits = [&](const float* out, const float* adv, const float* val, int a) {
+    if (rb) {
+      for (int k = tid; k < K; k += blockDim.x) {
+        float m = 0.f;
+        for (int aa = 0; aa < A; ++aa) m += adv[((long long)b * A + aa) * K + k];
+        m = m / (float)A;
+        logit[k] = val[(long long)b * K + k] + adv[((long long)b * A + a) * K + k] - m;
+      }
+    } else {
+      for (int k = tid; k < K; k += blockDim.x) logit[k] = out[((long long)b * A + a) * K + k];
+    }
+    __syncthreads();
+  };
+  // softmax statistics of `logit`
+  auto softmax_stats = [&](float& mx, float& denom) {
+    float m = -INFINITY;
+    for (int k = tid; k < K; k += blockDim.x) m = fmaxf(m, logit[k]);
+    mx = block_max(m, red);
+    float s = 0.f;
+    for (int k = tid; k < K; k += blockDim.x) s += expf(logit[k] - mx);
+    denom = block_sum(s, red);
+  };
+
+  // 1. selector q-values: c51 -> target net on s_t; rainbow -> online net on s_t (pass 1)
+  for (int a = 0; a < A; ++a) {
+    if (rb) load_logits(nullptr, L.adv1, L.val1, a); else load_logits(L.out2, nullptr, nullptr, a);
+    float mx, den;
+    softmax_stats(mx, den);
+    float s = 0.f;
+    for (int k = tid; k < K; k += blockDim.x) s += (expf(logit[k] - mx) / den) * support(k);
+    s = block_sum(s, red);
+    if (tid == 0) qsel[a] = s;
+    __syncthreads();
+  }
+  int best = 0;
+  for (int a = 1; a < A; ++a)
+    if (qsel[a] > qsel[best]) best = a;
+  // 2. target distribution p = softmax(target logits[a*])
+  if (rb) load_logits(nullptr, L.adv2, L.val2, best); else load_logits(L.out2, nullptr, nullptr, best);
+  {
+    float mx, den;
+    softmax_stats(mx, den);
+    for (int k = tid; k < K; k += blockDim.x) p_tgt[k] = expf(logit[k] - mx) / den;
+    __syncthreads();
+  }
+  // 3. rlax.categorical_l2_project(r + discount*z, p, z)
+  const float r = L.r[b], dsc = L.disc[b];
+  const float zmin = support(0), zmax = support(K - 1);
+  (void)dz_;
+  for (int i = tid; i < K; i += blockDim.x) {
+    float zi = support(i);
+    float dpos = (i + 1 < K ? support(i + 1) : support(0)) - zi;      // roll(z,-1) - z
+    float dneg = zi - (i > 0 ? support(i - 1) : support(K - 1));      // z - roll(z,1)
+    dpos = dpos > 0.f ? 1.0f / dpos : 0.f;
+    dneg = dneg > 0.f ? 1.0f / dneg : 0.f;
+    float acc = 0.f;
+    for (int j = 0; j < K; ++j) {
+      float zp = fminf(fmaxf(r + dsc * support(j), zmin), zmax);
+      float delta = zp - zi;
+      float dhat = delta >= 0.f ? delta * dpos : -(delta * dneg);
+      acc += fminf(fmaxf(1.0f - dhat, 0.f), 1.0f) * p_tgt[j];
+    }
+    proj[i] = acc;
+  }
+  __syncthreads();
+  // 4. cross entropy with log_softmax(logits_tm1[a_tm1])
+  const int at = L.a[b];
+  if (rb) load_logits(nullptr, L.adv0, L.val0, at); else load_logits(L.out0, nullptr, nullptr, at);
+  float mx, den;
+  softmax_stats(mx, den);
+  const float logden = logf(den);
+  float ls = 0.f, ps = 0.f;
+  for (int k = tid; k < K; k += blockDim.x) {
+    ls += proj[k] * (logit[k] - mx - logden);
+    ps += proj[k];
+  }
+  const float loss = -block_sum(ls, red);
+  const float psum = block_sum(ps, red);
+  const float w = L.w ? L.w[b] : 1.0f;
+  const float cot = w / (float)L.B;
+  // 5. gradient wrt the pass-0 head outputs
+  if (rb) {
+    for (int k = tid; k < K; k += blockDim.x) {
+      float dl = cot * (expf(logit[k] - mx) / den * psum - proj[k]);
+      L.dval[(long long)b * K + k] = dl;
+      for (int a = 0; a < A; ++a)
+        L.dadv[((long long)b * A + a) * K + k] = dl * ((a == at ? 1.0f : 0.0f) - 1.0f / (float)A);
+    }
+  } else {
+    for (int i = tid; i < A * K; i += blockDim.x) {
+      int a = i / K, k = i - a * K;
+      L.dout[(long long)b * A * K + i] = (a == at) ? cot * (expf(logit[k] - mx) / den * psum - proj[k]) : 0.f;
+    }
+  }
+  if (tid == 0) {
+    L.per_example[b] = loss;
+    if (L.priorities) L.priorities[b] = fminf(fmaxf(fabsf(loss), 0.f), 100.f);  // rainbow/agent.py:194
+    L.loss_terms[b] = w * loss;
+  }
+  (void)colmean;
+}
+
+// qrdqn / iqn: rlax.quantile_q_learning with quantile_regression_loss (Huber kappa).
+// Layouts: qrdqn out[b, q*A + a] (networks.py:308), iqn out[(b*N + n)*A + a] (networks.py:286-287).
+__global__ void __launch_bounds__(256) loss_quantile_kernel(LossArgs L) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.x, A = L.A, tid = threadIdx.x;
+  const bool iqn = L.kind == DZ_IQN;
+  const int N = L.N, Ks = L.Ksel, Nt = L.Nt;
+  float* red = sm;            // [32]
+  float* qsel = sm + 32;      // [A]
+  float* tgt = qsel + A;      // [Nt]
+  float* src = tgt + Nt;      // [N]
+  float* tau = src + N;       // [N]
+  // selector: mean over samples of the selector distribution (qrdqn: the target dist itself)
+  const float* sel = iqn ? L.out1 + (long long)b * Ks * A : L.out2 + (long long)b * Nt * A;
+  const int nsel = iqn ? Ks : Nt;
+  for (int a = 0; a < A; ++a) {
+    float s = 0.f;
+    for (int j = tid; j < nsel; j += blockDim.x) s += sel[(long long)j * A + a];
+    s = block_sum(s, red);
+    if (tid == 0) qsel[a] = s / (float)nsel;
+    __syncthreads();
+  }
+  int best = 0;
+  for (int a = 1; a < A; ++a)
+    if (qsel[a] > qsel[best]) best = a;
+  const int at = L.a[b];
+  const float r = L.r[b], dsc = L.disc[b];
+  const float* dist_t = L.out2 + (long long)b * Nt * A;
+  const float* dist_s = L.out0 + (long long)b * N * A;
+  for (int j = tid; j < Nt; j += blockDim.x) tgt[j] = r + dsc * dist_t[(long long)j * A + best];
+  for (int i = tid; i < N; i += blockDim.x) {
+    src[i] = dist_s[(long long)i * A + at];
+    tau[i] = iqn ? L.taus0[(long long)b * N + i] : ((float)i + 0.5f) / (float)N;  // qrdqn/run_atari.py:137
+  }
+  __syncthreads();
+  const float kappa = L.kappa;
+  const float w = L.w ? L.w[b] : 1.0f;
+  const float cot = w / (float)L.B;
+  float total = 0.f;
+  for (int i = tid; i < N; i += blockDim.x) {
+    float acc = 0.f, gacc = 0.f;
+    for (int j = 0; j < Nt; ++j) {
+      float delta = tgt[j] - src[i];
+      float wt = fabsf(tau[i] - (delta < 0.f ? 1.0f : 0.0f));
+      float ad = fabsf(delta);
+      float l, dl;
+      if (kappa > 0.f) {
+        float q = fminf(ad, kappa);
+        l = 0.5f * q * q + kappa * (ad - q);
+        dl = fminf(fmaxf(delta, -kappa), kappa);
+      } else {
+        l = ad;
+        dl = delta > 0.f ? 1.0f : (delta < 0.f ? -1.0f : 0.0f);
+      }
+      acc += wt * l;
+      gacc += wt * dl;
+    }
+    total += acc / (float)Nt;
+    float g = -cot * gacc / (float)Nt;  // d loss / d src_i  (delta = target - src)
+    for (int a = 0; a < A; ++a) L.dout[((long long)b * N + i) * A + a] = (a == at) ? g : 0.f;
+  }
+  total = block_sum(total, red);
+  if (tid == 0) {
+    L.per_example[b] = total;
+    L.loss_terms[b] = w * total;
+  }
+}
+
+__global__ void loss_mean_kernel(const float* __restrict__ terms, int B, float* loss, float* max_seen, const float* priorities) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += terms[b];
+    loss[0] = s / (float)B;
+    if (max_seen && priorities) {
+      float m = max_seen[0];
+      for (int b = 0; b < B; ++b) m = fmaxf(m, priorities[b]);
+      max_seen[0] = m;  // rainbow/agent.py:196-197
+    }
+  }
+}
+
+// q_values of one head pass (select_action): c51/rainbow expectation, qr/iqn mean, dqn identity.
+__global__ void __launch_bounds__(128) q_values_kernel(int kind, int A, int atoms, int nq, float vmax, const float* out,
+                                                       const float* adv, const float* val, float* q) {
+  extern __shared__ float sm[];
+  float* red = sm;
+  float* logit = sm + 32;
+  const int tid = threadIdx.x;
+  for (int a = 0; a < A; ++a) {
+    float res;
+    if (kind == DZ_C51 || kind == DZ_RAINBOW) {
+      const int K = atoms;
+      for (int k = tid; k < K; k += blockDim.x) {
+        if (kind == DZ_RAINBOW) {
+          float m = 0.f;
+          for (int aa = 0; aa < A; ++aa) m += adv[aa * K + k];
+          logit[k] = val[k] + adv[a * K + k] - m / (float)A;
+        } else {
+          logit[k] = out[a * K + k];
+        }
+      }
+      __syncthreads();
+      float m = -INFINITY;
+      for (int k = tid; k < K; k += blockDim.x) m = fmaxf(m, logit[k]);
+      m = block_max(m, red);
+      float s = 0.f, e = 0.f;
+      for (int k = tid; k < K; k += blockDim.x) {
+        float p = expf(logit[k] - m);
+        s += p;
+        e += p * (float)((double)(-vmax) + (double)k * (2.0 * (double)vmax / (double)(K - 1)));
+      }
+      s = block_sum(s, red);
+      e = block_sum(e, red);
+      res = e / s;
+    } else if (kind == DZ_QRDQN || kind == DZ_IQN) {
+      float s = 0.f;
+      for (int j = tid; j < nq; j += blockDim.x) s += out[(long long)j * A + a];
+      res = block_sum(s, red) / (float)nq;
+    } else {
+      res = out[a];
+    }
+    if (tid == 0) q[a] = res;
+    __syncthreads();
+  }
+}
+
+// ---- optimizer ---------------------------------------------------------------------------------
+
+// Sum of squares -> per-block partials; the last block to finish adds them in a fixed order
+// (deterministic), publishes the global norm and bumps the optimizer step count.
+__global__ void __launch_bounds__(256) grad_norm_kernel(const float* __restrict__ g, long long n, float* partials,
+                                                        unsigned int* ticket, float* norm_out, int64_t* counters, float* user_norm) {
+  __shared__ float s[32];
+  __shared__ bool last;
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = g[i];
+    acc = fmaf(v, v, acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += s[i];
+    partials[blockIdx.x] = t;
+    __threadfence();
+    unsigned int done = atomicAdd(ticket, 1u);
+    last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    float t = 0.f;
+    for (unsigned int i = 0; i < gridDim.x; ++i) t += ((volatile float*)partials)[i];
+    norm_out[0] = sqrtf(t);
+    if (user_norm) user_norm[0] = norm_out[0];
+    *ticket = 0;
+    counters[0] += 1;  // optax adam `count` (also counts rmsprop steps)
+  }
+}
+
+struct OptArgs {
+  int kind; float lr, eps, decay, b1, b2, max_norm;
+  float* p; const float* g; float* m; float* v; long long n; const float* norm; const int64_t* counters;
+};
+
+__global__ void __launch_bounds__(256) optimizer_kernel(OptArgs o) {
+  const float norm = o.norm[0];
+  const bool clip = o.max_norm > 0.f && !(norm < o.max_norm);  // optax.clip_by_global_norm trigger
+  float c1 = 1.f, c2 = 1.f;
+  if (o.kind == DZ_ADAM) {
+    float t = (float)o.counters[0];
+    c1 = 1.0f - powf(o.b1, t);
+    c2 = 1.0f - powf(o.b2, t);
+  }
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < o.n; i += (long long)gridDim.x * blockDim.x) {
+    float g = o.g[i];
+    if (clip) g = (g / norm) * o.max_norm;
+    float upd;
+    if (o.kind == DZ_ADAM) {  // optax.scale_by_adam: eps outside the sqrt, bias-corrected moments
+      float mu = o.b1 * o.m[i] + (1.0f - o.b1) * g;
+      float nu = o.b2 * o.v[i] + (1.0f - o.b2) * g * g;
+      o.m[i] = mu; o.v[i] = nu;
+      upd = (mu / c1) / (sqrtf(nu / c2) + o.eps);
+    } else {                  // optax.rmsprop(centered=True): eps inside the sqrt
+      float mu = o.decay * o.m[i] + (1.0f - o.decay) * g;
+      float nu = o.decay * o.v[i] + (1.0f - o.decay) * g * g;
+      o.m[i] = mu; o.v[i] = nu;
+      upd = g * (1.0f / sqrtf(nu - mu * mu + o.eps));
+    }
+    o.p[i] = o.p[i] - o.lr * upd;
+  }
+}
+
+__global__ void make_row_table_kernel(const uint8_t* base, long long stride, int n, const uint8_t** table) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) table[i] = base + (long long)i * stride;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// The learner object
+// ------------------------------------------------------------------------------------------------
+
+struct dz_learner {
+  dz_learner_config cfg;
+  dz_learner_buffers buf;
+  Layout lay;
+  Dims d;
+  int B;           // train batch
+  int n_head[3];   // rows per image in the head stage for pass 0/1/2 (IQN: tau samples; others 1)
+  // workspace (floats unless noted)
+  float *act1[3], *act2[3], *act3[3];
+  float *h1[3][2], *out[3], *outv[3];      // rainbow: h1[p][0]=adv stream, [1]=val stream; out=adv, outv=val
+  float *cosf[3], *hi[3], *E0;             // iqn
+  float* nn_partial;                        // split-K partials for the M=batch FC layers
+  float *dout, *doutv, *dh1[2], *dact3, *dtmp[2], *dcol, *dact2, *dact1, *dhi;
+  float* tn_partial[4];                     // conv1/2/3 wgrad partials, [3] = iqn head/embed partial
+  float *loss_terms, *scalars;              // scalars: [0]=norm, [1]=shared-bias scratch.., [8..]=norm partials
+  unsigned int* ticket;
+  const uint8_t** rows_sample[2];           // row tables filled by the fused sampler
+  const uint8_t** rows_act;                 // 1-entry table for q_values
+  int32_t* s_a; float *s_r, *s_d, *s_w;     // sampler-produced batch scalars
+  float *act_noise_zero;                    // zeros (acting without noise is never used; placeholder)
+  float* q_scratch;
+  int norm_blocks;
+  int fc_splits;
+};
+
+namespace {
+
+constexpr int kNormBlocks = 296;
+
+int64_t carve(dz_learner* l, char* base) {
+  const dz_learner_config& c = l->cfg;
+  const Dims& d = l->d;
+  const int B = c.batch;
+  Bump w{base};
+  const bool rb = c.kind == DZ_RAINBOW, iqn = c.kind == DZ_IQN;
+  int nh[3] = {1, 1, 1};
+  if (iqn) { nh[0] = c.tau_samples_s_tm1; nh[1] = c.tau_samples_policy; nh[2] = c.tau_samples_s_t; }
+  for (int p = 0; p < 3; ++p) l->n_head[p] = nh[p];
+  for (int p = 0; p < 3; ++p) {
+    l->act1[p] = w.take<float>((int64_t)B * d.h1 * d.w1 * 32);
+    l->act2[p] = w.take<float>((int64_t)B * d.h2 * d.w2 * 64);
+    l->act3[p] = w.take<float>((int64_t)B * d.feat);
+    int64_t rows = (int64_t)B * nh[p];
+    l->h1[p][0] = w.take<float>(rows * 512);
+    l->h1[p][1] = rb ? w.take<float>(rows * 512) : nullptr;
+    l->out[p] = w.take<float>(rows * d.out);
+    l->outv[p] = rb ? w.take<float>((int64_t)B * c.num_atoms) : nullptr;
+    l->cosf[p] = iqn ? w.take<float>(rows * c.latent_dim) : nullptr;
+    l->hi[p] = iqn ? w.take<float>(rows * d.feat) : nullptr;
+  }
+  l->E0 = iqn ? w.take<float>((int64_t)B * nh[0] * d.feat) : nullptr;
+  l->fc_splits = 14;
+  l->nn_partial = w.take<float>((int64_t)kMaxProblems * l->fc_splits * 2 * B * 512);
+  int64_t rows0 = (int64_t)B * nh[0];
+  l->dout = w.take<float>(rows0 * d.out);
+  l->doutv = rb ? w.take<float>((int64_t)B * c.num_atoms) : nullptr;
+  l->dh1[0] = w.take<float>(rows0 * 512);
+  l->dh1[1] = rb ? w.take<float>(rows0 * 512) : nullptr;
+  l->dact3 = w.take<float>((int64_t)B * d.feat);
+  l->dtmp[0] = rb ? w.take<float>((int64_t)B * d.feat) : nullptr;
+  l->dtmp[1] = rb ? w.take<float>((int64_t)B * d.feat) : nullptr;
+  int64_t col2 = (int64_t)B * d.h2 * d.w2 * 512, col3 = (int64_t)B * d.h3 * d.w3 * 576;
+  l->dcol = w.take<float>(col2 > col3 ? col2 : col3);
+  l->dact2 = w.take<float>((int64_t)B * d.h2 * d.w2 * 64);
+  l->dact1 = w.take<float>((int64_t)B * d.h1 * d.w1 * 32);
+  l->dhi = iqn ? w.take<float>(rows0 * d.feat) : nullptr;
+  l->tn_partial[0] = w.take<float>((int64_t)64 * 257 * 32);
+  l->tn_partial[1] = w.take<float>((int64_t)32 * 513 * 64);
+  l->tn_partial[2] = w.take<float>((int64_t)32 * 577 * 64);
+  l->tn_partial[3] = iqn ? w.take<float>((int64_t)16 * (c.latent_dim + 1) * d.feat + 16 * 513 * 64) : nullptr;
+  l->loss_terms = w.take<float>(B);
+  l->scalars = w.take<float>(8 + kNormBlocks + d.out + 64);
+  l->ticket = w.take<unsigned int>(4);
+  l->rows_sample[0] = w.take<const uint8_t*>(B);
+  l->rows_sample[1] = w.take<const uint8_t*>(B);
+  l->rows_act = w.take<const uint8_t*>(4);
+  l->s_a = w.take<int32_t>(B);
+  l->s_r = w.take<float>(B);
+  l->s_d = w.take<float>(B);
+  l->s_w = w.take<float>(B);
+  l->q_scratch = w.take<float>(64);
+  return w.used;
+}
+
+// Noise layout of ONE apply: adv1_in[feat] adv1_out[512] adv2_in[512] adv2_out[A*atoms] val1_in[feat]
+// val1_out[512] val2_in[512] val2_out[atoms]; every vector starts on a 4-float boundary.
+inline int64_t pad4(int64_t n) { return (n + 3) / 4 * 4; }
+int64_t noise_stride(const dz_learner_config& c, const Dims& d) {
+  return 2 * (pad4(d.feat) + 512 + 512) + pad4((int64_t)c.num_actions * c.num_atoms) + pad4(c.num_atoms);
+}
+struct NoiseVecs { const float *a1i, *a1o, *a2i, *a2o, *v1i, *v1o, *v2i, *v2o; };
+NoiseVecs noise_of(const dz_learner_config& c, const Dims& d, const float* base, int apply) {
+  const float* p = base + (int64_t)apply * noise_stride(c, d);
+  NoiseVecs n;
+  n.a1i = p; p += pad4(d.feat); n.a1o = p; p += 512; n.a2i = p; p += 512; n.a2o = p; p += pad4((int64_t)c.num_actions * c.num_atoms);
+  n.v1i = p; p += pad4(d.feat); n.v1o = p; p += 512; n.v2i = p; p += 512; n.v2o = p;
+  return n;
+}
+
+GemmProblem zero_problem() {
+  GemmProblem p;
+  memset(&p, 0, sizeof(p));
+  p.splits = 1;
+  p.mul_div = 1;
+  return p;
+}
+
+void set_conv(GemmProblem& p, int mode, const void* A, int nimg, int H, int W, int Cin, int KH, int KW, int S) {
+  p.a_mode = mode; p.A = A; p.H = H; p.W = W; p.Cin = Cin; p.KW = KW; p.S = S;
+  p.OH = conv_out(H, KH, S); p.OW = conv_out(W, KW, S);
+  p.seg = KW * Cin;
+  p.M = nimg * p.OH * p.OW;
+  p.K = KH * KW * Cin;
+}
+
+template <typename KernelT>
+int launch_batch(KernelT kernel, const GemmBatch& gb, dim3 grid, int threads, void* stream) {
+  DZ_LAUNCH(kernel, grid, threads, 0, stream, gb);
+  return DZ_OK;
+}
+
+#define DZ_TRY(expr) do { int _s = (expr); if (_s != DZ_OK) return _s; } while (0)
+
+// ---- NN launch helpers (tile shapes chosen by M / N) -------------------------------------------
+
+int run_nn(GemmBatch& gb, bool dual, void* stream) {
+  int maxM = 0, maxN = 0, maxS = 1;
+  for (int i = 0; i < gb.n; ++i) {
+    maxM = gb.p[i].M > maxM ? gb.p[i].M : maxM;
+    maxN = gb.p[i].N > maxN ? gb.p[i].N : maxN;
+    maxS = gb.p[i].splits > maxS ? gb.p[i].splits : maxS;
+  }
+  if (maxM <= 32) {
+    dim3 grid((unsigned)ceil_div(maxN, 64), (unsigned)(ceil_div(maxM, 32) * maxS), gb.n);
+    if (dual) return launch_batch(gemm_nn_kernel<32, 64, 16, 2, 4, true>, gb, grid, 256, stream);
+    return launch_batch(gemm_nn_kernel<32, 64, 16, 2, 4, false>, gb, grid, 256, stream);
+  }
+  if (maxN <= 32 && !dual) {
+    dim3 grid(1, (unsigned)(ceil_div(maxM, 128) * maxS), gb.n);
+    return launch_batch(gemm_nn_kernel<128, 32, 16, 4, 4, false>, gb, grid, 256, stream);
+  }
+  dim3 grid((unsigned)ceil_div(maxN, 64), (unsigned)(ceil_div(maxM, 64) * maxS), gb.n);
+  if (dual) return launch_batch(gemm_nn_kernel<64, 64, 16, 4, 4, true>, gb, grid, 256, stream);
+  return launch_batch(gemm_nn_kernel<64, 64, 16, 4, 4, false>, gb, grid, 256, stream);
+}
+
+int run_tn(GemmBatch& gb, void* stream) {
+  int maxK = 0, maxN = 0, maxS = 1;
+  for (int i = 0; i < gb.n; ++i) {
+    int kext = gb.p[i].K + ((gb.p[i].Cb || gb.p[i].Cb2) ? 1 : 0);
+    maxK = kext > maxK ? kext : maxK;
+    maxN = gb.p[i].N > maxN ? gb.p[i].N : maxN;
+    maxS = gb.p[i].splits > maxS ? gb.p[i].splits : maxS;
+  }
+  if (maxN <= 32) {
+    dim3 grid(1, (unsigned)(ceil_div(maxK, 64) * maxS), gb.n);
+    return launch_batch(gemm_tn_kernel<64, 32, 16, 4, 2>, gb, grid, 256, stream);
+  }
+  dim3 grid((unsigned)ceil_div(maxN, 64), (unsigned)(ceil_div(maxK, 64) * maxS), gb.n);
+  return launch_batch(gemm_tn_kernel<64, 64, 16, 4, 4>, gb, grid, 256, stream);
+}
+
+int run_nt(GemmBatch& gb, bool dual, void* stream) {
+  int maxM = 0, maxK = 0;
+  for (int i = 0; i < gb.n; ++i) {
+    maxM = gb.p[i].M > maxM ? gb.p[i].M : maxM;
+    maxK = gb.p[i].K > maxK ? gb.p[i].K : maxK;
+  }
+  if (maxM <= 32) {
+    dim3 grid((unsigned)ceil_div(maxK, 64), (unsigned)ceil_div(maxM, 32), gb.n);
+    if (dual) return launch_batch(gemm_nt_kernel<32, 64, 16, 2, 4, true>, gb, grid, 256, stream);
+    return launch_batch(gemm_nt_kernel<32, 64, 16, 2, 4, false>, gb, grid, 256, stream);
+  }
+  dim3 grid((unsigned)ceil_div(maxK, 64), (unsigned)ceil_div(maxM, 64), gb.n);
+  if (dual) return launch_batch(gemm_nt_kernel<64, 64, 16, 4, 4, true>, gb, grid, 256, stream);
+  return launch_batch(gemm_nt_kernel<64, 64, 16, 4, 4, false>, gb, grid, 256, stream);
+}
+
+int finish_nn(const GemmBatch& gb, float* const* outs, bool dual, void* stream) {
+  FinishNNBatch fb;
+  fb.n = gb.n;
+  long long mx = 0;
+  for (int i = 0; i < gb.n; ++i) {
+    const GemmProblem& p = gb.p[i];
+    fb.f[i] = FinishNN{p.C, p.splits, p.split_stride, p.M, p.N, dual ? 1 : 0, p.bias, p.bias2, p.c_scale, p.relu, p.bias_shared, outs[i]};
+    long long t = (long long)p.M * p.N;
+    mx = t > mx ? t : mx;
+  }
+  dim3 grid((unsigned)ceil_div(mx, 256), gb.n);
+  DZ_LAUNCH(finish_nn_kernel, grid, 256, 0, stream, fb);
+  return DZ_OK;
+}
+
+struct Pass {        // one network.apply
+  const float* params;     // online or target blob
+  const uint8_t* const* rows;  // image row table
+  int set;                 // torso activation set index (0..2)
+  int head;                // head pass index (0..2)
+  int apply;               // noise apply index (rainbow)
+};
+
+// ---- forward -----------------------------------------------------------------------------------
+
+struct TorsoJob { const float* params; const uint8_t* const* rows; int set; };
+
+int forward_torso(dz_learner* l, const TorsoJob* jobs, int njobs, int nimg, void* stream) {
+  const Dims& d = l->d;
+  const Layout& L = l->lay;
+  GemmBatch gb;
+  gb.n = njobs;
+  for (int i = 0; i < njobs; ++i) {   // conv1: uint8 rows gathered in place (K1 + K2 of SURVEY §2.1)
+    GemmProblem p = zero_problem();
+    set_conv(p, A_CONV_U8, jobs[i].rows, nimg, d.H, d.W, d.C, 8, 8, 4);
+    p.B = jobs[i].params + L.off("conv1/w"); p.bias = jobs[i].params + L.off("conv1/b");
+    p.N = 32; p.ldb = 32; p.ldc = 32; p.relu = 1; p.C = l->act1[jobs[i].set];
+    gb.p[i] = p;
+  }
+  DZ_TRY(run_nn(gb, false, stream));
+  for (int i = 0; i < njobs; ++i) {   // conv2
+    GemmProblem p = zero_problem();
+    set_conv(p, A_CONV_F32, l->act1[jobs[i].set], nimg, d.h1, d.w1, 32, 4, 4, 2);
+    p.B = jobs[i].params + L.off("conv2/w"); p.bias = jobs[i].params + L.off("conv2/b");
+    p.N = 64; p.ldb = 64; p.ldc = 64; p.relu = 1; p.C = l->act2[jobs[i].set];
+    gb.p[i] = p;
+  }
+  DZ_TRY(run_nn(gb, false, stream));
+  for (int i = 0; i < njobs; ++i) {   // conv3
+    GemmProblem p = zero_problem();
+    set_conv(p, A_CONV_F32, l->act2[jobs[i].set], nimg, d.h2, d.w2, 64, 3, 3, 1);
+    p.B = jobs[i].params + L.off("conv3/w"); p.bias = jobs[i].params + L.off("conv3/b");
+    p.N = 64; p.ldb = 64; p.ldc = 64; p.relu = 1; p.C = l->act3[jobs[i].set];
+    gb.p[i] = p;
+  }
+  DZ_TRY(run_nn(gb, false, stream));
+  return DZ_OK;
+}
+
+// Heads for the dqn / double_q / prioritized / c51 / qrdqn family.
+int forward_heads_plain(dz_learner* l, const Pass* passes, int np, int nimg, void* stream) {
+  const Dims& d = l->d;
+  const Layout& L = l->lay;
+  GemmBatch gb;
+  gb.n = np;
+  float* outs[kMaxProblems];
+  const bool shared = l->cfg.kind == DZ_DOUBLE_Q || l->cfg.kind == DZ_PRIORITIZED;
+  const int splits = nimg <= 32 ? l->fc_splits : 1;
+  for (int i = 0; i < np; ++i) {
+    GemmProblem p = zero_problem();
+    p.a_mode = A_PLAIN; p.A = l->act3[passes[i].set]; p.lda = d.feat; p.M = nimg; p.K = d.feat;
+    p.B = passes[i].params + L.off("fc1/w"); p.N = 512; p.ldb = 512; p.ldc = 512;
+    p.bias = passes[i].params + L.off("fc1/b"); p.relu = 1;
+    outs[i] = l->h1[passes[i].head][0];
+    if (splits > 1) {
+      p.splits = splits; p.split_stride = (long long)nimg * 512;
+      p.C = l->nn_partial + (long long)i * splits * p.split_stride;
+    } else {
+      p.C = outs[i];
+    }
+    gb.p[i] = p;
+  }
+  DZ_TRY(run_nn(gb, false, stream));
+  if (splits > 1) DZ_TRY(finish_nn(gb, outs, false, stream));
+  for (int i = 0; i < np; ++i) {
+    GemmProblem p = zero_problem();
+    p.a_mode = A_PLAIN; p.A = l->h1[passes[i].head][0]; p.lda = 512; p.M = nimg; p.K = 512;
+    p.B = passes[i].params + L.off("head/w"); p.N = d.out; p.ldb = d.out; p.ldc = d.out;
+    p.bias = passes[i].params + L.off("head/b"); p.bias_shared = shared ? 1 : 0;
+    p.C = l->out[passes[i].head];
+    gb.p[i] = p;
+  }
+  DZ_TRY(run_nn(gb, false, stream));
+  return DZ_OK;
+}
+
+// Rainbow: two noisy streams (networks.py:224-261, :137-178).
+int forward_heads_rainbow(dz_learner* l, const Pass* passes, int np, int nimg, const float* noise, void* stream) {
+  const Dims& d = l->d;
+  const Layout& L = l->lay;
+  const dz_learner_config& c = l->cfg;
+  if (2 * np > kMaxProblems) return fail(DZ_EINVAL, "too many rainbow passes");
+  GemmBatch gb;
+  gb.n = 2 * np;
+  float* outs[kMaxProblems];
+  const int splits = nimg <= 32 ? l->fc_splits : 1;
+  const char* st[2] = {"adv", "val"};
+  for (int i = 0; i < np; ++i) {
+    NoiseVecs nz = noise_of(c, d, noise, passes[i].apply);
+    for (int s = 0; s < 2; ++s) {
+      std::string pre = std::string(st[s]) + "1/";
+      GemmProblem p = zero_problem();
+      p.a_mode = A_PLAIN; p.A = l->act3[passes[i].set]; p.lda = d.feat; p.M = nimg; p.K = d.feat;
+      p.B = passes[i].params + L.off(pre + "mu/w"); p.B2 = passes[i].params + L.off(pre + "sigma/w");
+      p.N = 512; p.ldb = 512; p.ldc = 512;
+      p.bias = passes[i].params + L.off(pre + "mu/b"); p.bias2 = passes[i].params + L.off(pre + "sigma/b");
+      p.a_scale = s == 0 ? nz.a1i : nz.v1i; p.c_scale = s == 0 ? nz.a1o : nz.v1o; p.relu = 1;
+      int q = 2 * i + s;
+      outs[q] = l->h1[passes[i].head][s];
+      if (splits > 1) {
+        p.splits = splits; p.split_stride = (long long)2 * nimg * 512;
+        p.C = l->nn_partial + (long long)q * splits * p.split_stride;
+      } else {
+        p.C = outs[q];
+      }
+      gb.p[q] = p;
+    }
+  }
+  DZ_TRY(run_nn(gb, true, stream));
+  if (splits > 1) DZ_TRY(finish_nn(gb, outs, true, stream));
+  for (int i = 0; i < np; ++i) {
+    NoiseVecs nz = noise_of(c, d, noise, passes[i].apply);
+    for (int s = 0; s < 2; ++s) {
+      std::string pre = std::string(st[s]) + "2/";
+      int n_out = s == 0 ? c.num_actions * c.num_atoms : c.num_atoms;
+      GemmProblem p = zero_problem();
+      p.a_mode = A_PLAIN; p.A = l->h1[passes[i].head][s]; p.lda = 512; p.M = nimg; p.K = 512;
+      p.B = passes[i].params + L.off(pre + "mu/w"); p.B2 = passes[i].params + L.off(pre + "sigma/w");
+      p.N = n_out; p.ldb = n_out; p.ldc = n_out;
+      p.bias = nullptr; p.bias2 = passes[i].params + L.off(pre + "sigma/b");   // with_bias=False: mu has no bias
+      p.a_scale = s == 0 ? nz.a2i : nz.v2i; p.c_scale = s == 0 ? nz.a2o : nz.v2o;
+      p.C = s == 0 ? l->out[passes[i].head] : l->outv[passes[i].head];
+      gb.p[2 * i + s] = p;
+    }
+  }
+  DZ_TRY(run_nn(gb, true, stream));
+  return DZ_OK;
+}
+
+// IQN (networks.py:264-292): cosine embedding -> linear -> relu -> * state embedding -> value head.
+int forward_heads_iqn(dz_learner* l, const Pass* passes, int np, int nimg, const float* const* taus, bool keep_E0, void* stream) {
+  const Dims& d = l->d;
+  const Layout& L = l->lay;
+  const dz_learner_config& c = l->cfg;
+  GemmBatch gb;
+  gb.n = np;
+  for (int i = 0; i < np; ++i) {
+    long long rows = (long long)nimg * l->n_head[passes[i].head];
+    DZ_LAUNCH(iqn_cos_kernel, (unsigned)ceil_div(rows * c.latent_dim, 256), 256, 0, stream, taus[i], l->cosf[passes[i].head],
+              rows, c.latent_dim);
+  }
+  for (int i = 0; i < np; ++i) {
+    int hp = passes[i].head;
+    GemmProblem p = zero_problem();
+    p.a_mode = A_PLAIN; p.A = l->cosf[hp]; p.lda = c.latent_dim; p.M = nimg * l->n_head[hp]; p.K = c.latent_dim;
+    p.B = passes[i].params + L.off("embed/w"); p.N = d.feat; p.ldb = d.feat; p.ldc = d.feat;
+    p.bias = passes[i].params + L.off("embed/b"); p.relu = 1;
+    p.mul = l->act3[passes[i].set]; p.mul_div = l->n_head[hp];
+    p.C = l->hi[hp]; p.C2 = (keep_E0 && hp == 0) ? l->E0 : nullptr;
+    gb.p[i] = p;
+  }
+  DZ_TRY(run_nn(gb, false, stream));
+  for (int i = 0; i < np; ++i) {
+    int hp = passes[i].head;
+    GemmProblem p = zero_problem();
+    p.a_mode = A_PLAIN; p.A = l->hi[hp]; p.lda = d.feat; p.M = nimg * l->n_head[hp]; p.K = d.feat;
+    p.B = passes[i].params + L.off("fc1/w"); p.N = 512; p.ldb = 512; p.ldc = 512;
+    p.bias = passes[i].params + L.off("fc1/b"); p.relu = 1; p.C = l->h1[hp][0];
+    gb.p[i] = p;
+  }
+  // M can be small when acting (1 x tau_samples_policy rows): same kernel family handles it
+  DZ_TRY(run_nn(gb, false, stream));
+  for (int i = 0; i < np; ++i) {
+    int hp = passes[i].head;
+    GemmProblem p = zero_problem();
+    p.a_mode = A_PLAIN; p.A = l->h1[hp][0]; p.lda = 512; p.M = nimg * l->n_head[hp]; p.K = 512;
+    p.B = passes[i].params + L.off("head/w"); p.N = d.out; p.ldb = d.out; p.ldc = d.out;
+    p.bias = passes[i].params + L.off("head/b"); p.C = l->out[hp];
+    gb.p[i] = p;
+  }
+  DZ_TRY(run_nn(gb, false, stream));
+  return DZ_OK;
+}
+
+// ---- backward ----------------------------------------------------------------------------------
+
+// Torso backward from dact3 (already masked by act3 > 0): conv3/conv2/conv1 weight+bias grads.
+int backward_torso(dz_learner* l, const uint8_t* const* rows0, void* stream) {
+  const Dims& d = l->d;
+  const Layout& L = l->lay;
+  const int B = l->B;
+  float* G = l->buf.d_grads;
+  const float* P = l->buf.d_online;
+  FinishTNBatch fb;
+  fb.n = 0;
+  GemmBatch gb;
+  // conv3 wgrad
+  {
+    GemmProblem p = zero_problem();
+    set_conv(p, A_CONV_F32, l->act2[0], B, d.h2, d.w2, 64, 3, 3, 1);
+    p.B = l->dact3; p.N = 64; p.ldb = 64; p.ldc = 64;
+    p.Cb = G + L.off("conv3/b");
+    int splits = (int)std::min<int64_t>(32, ceil_div(p.M, 64));
+    p.splits = splits; p.split_stride = (long long)(p.K + 1) * 64; p.C = l->tn_partial[2];
+    gb.n = 1; gb.p[0] = p;
+    DZ_TRY(run_tn(gb, stream));
+    fb.f[fb.n++] = FinishTN{p.C, splits, p.split_stride, p.K, 64, G + L.off("conv3/w"), nullptr, p.Cb, nullptr, nullptr, nullptr};
+  }
+  // conv3 dgrad: dcol = dpre3 * W3^T ; col2im with ReLU mask of act2
+  {
+    GemmProblem p = zero_problem();
+    p.A = l->dact3; p.lda = 64; p.M = B * d.h3 * d.w3; p.N = 64; p.K = 576;
+    p.B = P + L.off("conv3/w"); p.ldb = 64; p.C = l->dcol; p.ldc = 576;
+    gb.n = 1; gb.p[0] = p;
+    DZ_TRY(run_nt(gb, false, stream));
+    long long total = (long long)B * d.h2 * d.w2 * 64;
+    DZ_LAUNCH(col2im_kernel, (unsigned)ceil_div(total, 256), 256, 0, stream, l->dcol, l->act2[0], l->dact2, B, d.h2, d.w2, 64, 3, 3, 1,
+              d.h3, d.w3);
+  }
+  // conv2 wgrad
+  {
+    GemmProblem p = zero_problem();
+    set_conv(p, A_CONV_F32, l->act1[0], B, d.h1, d.w1, 32, 4, 4, 2);
+    p.B = l->dact2; p.N = 64; p.ldb = 64; p.ldc = 64;
+    p.Cb = G + L.off("conv2/b");
+    int splits = (int)std::min<int64_t>(32, ceil_div(p.M, 64));
+    p.splits = splits; p.split_stride = (long long)(p.K + 1) * 64; p.C = l->tn_partial[1];
+    gb.n = 1; gb.p[0] = p;
+    DZ_TRY(run_tn(gb, stream));
+    fb.f[fb.n++] = FinishTN{p.C, splits, p.split_stride, p.K, 64, G + L.off("conv2/w"), nullptr, p.Cb, nullptr, nullptr, nullptr};
+  }
+  // conv2 dgrad
+  {
+    GemmProblem p = zero_problem();
+    p.A = l->dact2; p.lda = 64; p.M = B * d.h2 * d.w2; p.N = 64; p.K = 512;
+    p.B = P + L.off("conv2/w"); p.ldb = 64; p.C = l->dcol; p.ldc = 512;
+    gb.n = 1; gb.p[0] = p;
+    DZ_TRY(run_nt(gb, false, stream));
+    long long total = (long long)B * d.h1 * d.w1 * 32;
+    DZ_LAUNCH(col2im_kernel, (unsigned)ceil_div(total, 256), 256, 0, stream, l->dcol, l->act1[0], l->dact1, B, d.h1, d.w1, 32, 4, 4, 2,
+              d.h2, d.w2);
+  }
+  // conv1 wgrad (A = uint8 rows in place)
+  {
+    GemmProblem p = zero_problem();
+    set_conv(p, A_CONV_U8, rows0, B, d.H, d.W, d.C, 8, 8, 4);
+    p.B = l->dact1; p.N = 32; p.ldb = 32; p.ldc = 32;
+    p.Cb = G + L.off("conv1/b");
+    int splits = (int)std::min<int64_t>(64, ceil_div(p.M, 64));
+    p.splits = splits; p.split_stride = (long long)(p.K + 1) * 32; p.C = l->tn_partial[0];
+    gb.n = 1; gb.p[0] = p;
+    DZ_TRY(run_tn(gb, stream));
+    fb.f[fb.n++] = FinishTN{p.C, splits, p.split_stride, p.K, 32, G + L.off("conv1/w"), nullptr, p.Cb, nullptr, nullptr, nullptr};
+  }
+  dim3 grid((unsigned)ceil_div(577 * 64, 256), fb.n);
+  DZ_LAUNCH(finish_tn_kernel, grid, 256, 0, stream, fb);
+  return DZ_OK;
+}
+
+int backward_plain(dz_learner* l, void* stream) {
+  const Dims& d = l->d;
+  const Layout& L = l->lay;
+  const int B = l->B;
+  float* G = l->buf.d_grads;
+  const float* P = l->buf.d_online;
+  const bool shared = l->cfg.kind == DZ_DOUBLE_Q || l->cfg.kind == DZ_PRIORITIZED;
+  GemmBatch gb;
+  gb.n = 1;
+  {  // head wgrad
+    GemmProblem p = zero_problem();
+    p.a_mode = A_PLAIN; p.A = l->h1[0][0]; p.lda = 512; p.M = B; p.K = 512;
+    p.B = l->dout; p.N = d.out; p.ldb = d.out; p.ldc = d.out;
+    p.C = G + L.off("head/w"); p.Cb = shared ? l->scalars + 8 + kNormBlocks : G + L.off("head/b");
+    gb.p[0] = p;
+    DZ_TRY(run_tn(gb, stream));
+    if (shared) DZ_LAUNCH(sum_to_scalar_kernel, 1, 128, 0, stream, l->scalars + 8 + kNormBlocks, d.out, G + L.off("head/b"));
+  }
+  {  // dh1 = dout * Wh^T, masked by h1 > 0
+    GemmProblem p = zero_problem();
+    p.A = l->dout; p.lda = d.out; p.M = B; p.N = d.out; p.K = 512;
+    p.B = P + L.off("head/w"); p.ldb = d.out; p.C = l->dh1[0]; p.ldc = 512; p.mask = l->h1[0][0];
+    gb.p[0] = p;
+    DZ_TRY(run_nt(gb, false, stream));
+  }
+  {  // fc1 wgrad
+    GemmProblem p = zero_problem();
+    p.a_mode = A_PLAIN; p.A = l->act3[0]; p.lda = d.feat; p.M = B; p.K = d.feat;
+    p.B = l->dh1[0]; p.N = 512; p.ldb = 512; p.ldc = 512;
+    p.C = G + L.off("fc1/w"); p.Cb = G + L.off("fc1/b");
+    gb.p[0] = p;
+    DZ_TRY(run_tn(gb, stream));
+  }
+  {  // dact3 = dh1 * Wf^T, masked by act3 > 0
+    GemmProblem p = zero_problem();
+    p.A = l->dh1[0]; p.lda = 512; p.M = B; p.N = 512; p.K = d.feat;
+    p.B = P + L.off("fc1/w"); p.ldb = 512; p.C = l->dact3; p.ldc = d.feat; p.mask = l->act3[0];
+    gb.p[0] = p;
+    DZ_TRY(run_nt(gb, false, stream));
+  }
+  return DZ_OK;
+}
+
+int backward_rainbow(dz_learner* l, const float* noise, void* stream) {
+  const Dims& d = l->d;
+  const Layout& L = l->lay;
+  const dz_learner_config& c = l->cfg;
+  const int B = l->B;
+  float* G = l->buf.d_grads;
+  const float* P = l->buf.d_online;
+  NoiseVecs nz = noise_of(c, d, noise, 0);
+  const char* st[2] = {"adv", "val"};
+  GemmBatch gb;
+  gb.n = 2;
+  for (int s = 0; s < 2; ++s) {  // second noisy layer weight grads
+    std::string pre = std::string(st[s]) + "2/";
+    int n_out = s == 0 ? c.num_actions * c.num_atoms : c.num_atoms;
+    GemmProblem p = zero_problem();
+    p.a_mode = A_PLAIN; p.A = l->h1[0][s]; p.lda = 512; p.M = B; p.K = 512;
+    p.B = s == 0 ? l->dout : l->doutv; p.N = n_out; p.ldb = n_out; p.ldc = n_out;
+    p.C = G + L.off(pre + "mu/w"); p.C2 = G + L.off(pre + "sigma/w"); p.Cb = nullptr; p.Cb2 = G + L.off(pre + "sigma/b");
+    p.a_scale = s == 0 ? nz.a2i : nz.v2i; p.c_scale = s == 0 ? nz.a2o : nz.v2o;
+    gb.p[s] = p;
+  }
+  DZ_TRY(run_tn(gb, stream));
+  for (int s = 0; s < 2; ++s) {  // dh1_s
+    std::string pre = std::string(st[s]) + "2/";
+    int n_out = s == 0 ? c.num_actions * c.num_atoms : c.num_atoms;
+    GemmProblem p = zero_problem();
+    p.A = s == 0 ? l->dout : l->doutv; p.lda = n_out; p.M = B; p.N = n_out; p.K = 512;
+    p.B = P + L.off(pre + "mu/w"); p.B2 = P + L.off(pre + "sigma/w"); p.ldb = n_out;
+    p.a_scale = s == 0 ? nz.a2i : nz.v2i; p.c_scale = s == 0 ? nz.a2o : nz.v2o;
+    p.C = l->dh1[s]; p.ldc = 512; p.mask = l->h1[0][s];
+    gb.p[s] = p;
+  }
+  DZ_TRY(run_nt(gb, true, stream));
+  for (int s = 0; s < 2; ++s) {  // first noisy layer weight grads
+    std::string pre = std::string(st[s]) + "1/";
+    GemmProblem p = zero_problem();
+    p.a_mode = A_PLAIN; p.A = l->act3[0]; p.lda = d.feat; p.M = B; p.K = d.feat;
+    p.B = l->dh1[s]; p.N = 512; p.ldb = 512; p.ldc = 512;
+    p.C = G + L.off(pre + "mu/w"); p.C2 = G + L.off(pre + "sigma/w"); p.Cb = G + L.off(pre + "mu/b"); p.Cb2 = G + L.off(pre + "sigma/b");
+    p.a_scale = s == 0 ? nz.a1i : nz.v1i; p.c_scale = s == 0 ? nz.a1o : nz.v1o;
+    gb.p[s] = p;
+  }
+  DZ_TRY(run_tn(gb, stream));
+  for (int s = 0; s < 2; ++s) {  // dact3 contributions
+    std::string pre = std::string(st[s]) + "1/";
+    GemmProblem p = zero_problem();
+    p.A = l->dh1[s]; p.lda = 512; p.M = B; p.N = 512; p.K = d.feat;
+    p.B = P + L.off(pre + "mu/w"); p.B2 = P + L.off(pre + "sigma/w"); p.ldb = 512;
+    p.a_scale = s == 0 ? nz.a1i : nz.v1i; p.c_scale = s == 0 ? nz.a1o : nz.v1o;
+    p.C = l->dtmp[s]; p.ldc = d.feat;
+    gb.p[s] = p;
+  }
+  DZ_TRY(run_nt(gb, true, stream));
+  long long n = (long long)B * d.feat;
+  DZ_LAUNCH(add_mask_kernel, (unsigned)ceil_div(n, 256), 256, 0, stream, l->dtmp[0], l->dtmp[1], l->act3[0], l->dact3, n);
+  return DZ_OK;
+}
+
+int backward_iqn(dz_learner* l, void* stream) {
+  const Dims& d = l->d;
+  const Layout& L = l->lay;
+  const dz_learner_config& c = l->cfg;
+  const int B = l->B, N = l->n_head[0], M = B * N;
+  float* G = l->buf.d_grads;
+  const float* P = l->buf.d_online;
+  GemmBatch gb;
+  gb.n = 1;
+  FinishTNBatch fb;
+  fb.n = 0;
+  float* part_head = l->tn_partial[3];
+  float* part_embed = l->tn_partial[3] + (long long)16 * 513 * 64;
+  {  // head wgrad: reduction over M rows
+    GemmProblem p = zero_problem();
+    p.a_mode = A_PLAIN; p.A = l->h1[0][0]; p.lda = 512; p.M = M; p.K = 512;
+    p.B = l->dout; p.N = d.out; p.ldb = d.out; p.ldc = d.out;
+    p.Cb = G + L.off("head/b");
+    int splits = (int)std::min<int64_t>(16, ceil_div(M, 64));
+    p.splits = splits; p.split_stride = (long long)513 * d.out; p.C = part_head;
+    gb.p[0] = p;
+    DZ_TRY(run_tn(gb, stream));
+    fb.f[fb.n++] = FinishTN{p.C, splits, p.split_stride, 512, d.out, G + L.off("head/w"), nullptr, p.Cb, nullptr, nullptr, nullptr};
+  }
+  {  // dh1
+    GemmProblem p = zero_problem();
+    p.A = l->dout; p.lda = d.out; p.M = M; p.N = d.out; p.K = 512;
+    p.B = P + L.off("head/w"); p.ldb = d.out; p.C = l->dh1[0]; p.ldc = 512; p.mask = l->h1[0][0];
+    gb.p[0] = p;
+    DZ_TRY(run_nt(gb, false, stream));
+  }
+  {  // fc1 wgrad (reduction over M rows, no split: 400 tiles already)
+    GemmProblem p = zero_problem();
+    p.a_mode = A_PLAIN; p.A = l->hi[0]; p.lda = d.feat; p.M = M; p.K = d.feat;
+    p.B = l->dh1[0]; p.N = 512; p.ldb = 512; p.ldc = 512;
+    p.C = G + L.off("fc1/w"); p.Cb = G + L.off("fc1/b");
+    gb.p[0] = p;
+    DZ_TRY(run_tn(gb, stream));
+  }
+  {  // dHI = dh1 * Wf^T
+    GemmProblem p = zero_problem();
+    p.A = l->dh1[0]; p.lda = 512; p.M = M; p.N = 512; p.K = d.feat;
+    p.B = P + L.off("fc1/w"); p.ldb = 512; p.C = l->dhi; p.ldc = d.feat;
+    gb.p[0] = p;
+    DZ_TRY(run_nt(gb, false, stream));
+  }
+  DZ_LAUNCH(iqn_hadamard_bwd_kernel, (unsigned)ceil_div((long long)B * d.feat, 256), 256, 0, stream, l->dhi, l->E0, l->act3[0],
+            l->dact3, B, N, d.feat);
+  {  // embed wgrad: [latent, feat] = cos^T * dE
+    GemmProblem p = zero_problem();
+    p.a_mode = A_PLAIN; p.A = l->cosf[0]; p.lda = c.latent_dim; p.M = M; p.K = c.latent_dim;
+    p.B = l->dhi; p.N = d.feat; p.ldb = d.feat; p.ldc = d.feat;
+    p.Cb = G + L.off("embed/b");
+    int splits = (int)std::min<int64_t>(16, ceil_div(M, 64));
+    p.splits = splits; p.split_stride = (long long)(c.latent_dim + 1) * d.feat; p.C = part_embed;
+    gb.p[0] = p;
+    DZ_TRY(run_tn(gb, stream));
+    fb.f[fb.n++] = FinishTN{p.C, splits, p.split_stride, c.latent_dim, d.feat, G + L.off("embed/w"), nullptr, p.Cb, nullptr, nullptr, nullptr};
+  }
+  long long mx = std::max<long long>((long long)513 * d.out, (long long)(c.latent_dim + 1) * d.feat);
+  dim3 grid((unsigned)ceil_div(mx, 256), fb.n);
+  DZ_LAUNCH(finish_tn_kernel, grid, 256, 0, stream, fb);
+  return DZ_OK;
+}
+
+int run_optimizer(dz_learner* l, float* user_norm, bool apply, void* stream) {
+  const dz_learner_config& c = l->cfg;
+  long long n = l->lay.total;
+  float* norm = l->scalars;
+  DZ_LAUNCH(grad_norm_kernel, kNormBlocks, 256, 0, stream, l->buf.d_grads, n, l->scalars + 8, l->ticket, norm,
+            apply ? l->buf.d_counters : l->buf.d_counters + 3, user_norm);
+  if (!apply) return DZ_OK;
+  OptArgs o{c.optimizer, c.learning_rate, c.opt_eps, c.rms_decay, c.adam_b1, c.adam_b2, c.max_global_grad_norm,
+            l->buf.d_online, l->buf.d_grads, l->buf.d_opt_state, l->buf.d_opt_state + n, n, norm, l->buf.d_counters};
+  DZ_LAUNCH(optimizer_kernel, 592, 256, 0, stream, o);
+  return DZ_OK;
+}
+
+int update_impl(dz_learner* l, const dz_batch* batch, const dz_update_outputs* out, int apply_update, float* max_seen,
+                void* stream) {
+  const dz_learner_config& c = l->cfg;
+  const Dims& d = l->d;
+  const int B = l->B;
+  const float* on = l->buf.d_online;
+  const float* tg = l->buf.d_target;
+  const bool needs_online_st = c.kind == DZ_DOUBLE_Q || c.kind == DZ_PRIORITIZED || c.kind == DZ_RAINBOW;
+  if (c.kind == DZ_RAINBOW && !batch->d_noise) return fail(DZ_EINVAL, "rainbow update needs d_noise");
+  if (c.kind == DZ_IQN && !batch->d_taus) return fail(DZ_EINVAL, "iqn update needs d_taus");
+  if (!out || !out->d_loss || !out->d_per_example) return fail(DZ_EINVAL, "update outputs d_loss and d_per_example are required");
+
+  // ---- forward: every network.apply of loss_fn in grouped launches
+  TorsoJob jobs[3];
+  int nj = 0;
+  jobs[nj++] = TorsoJob{on, batch->d_s_tm1_rows, 0};
+  if (needs_online_st) jobs[nj++] = TorsoJob{on, batch->d_s_t_rows, 1};
+  jobs[nj++] = TorsoJob{tg, batch->d_s_t_rows, 2};
+  DZ_TRY(forward_torso(l, jobs, nj, B, stream));
+
+  if (c.kind == DZ_IQN) {
+    // online(s_tm1, tau_tm1) | target(s_t, tau_selector) | target(s_t, tau_t)   (iqn/agent.py:192-203)
+    Pass passes[3] = {{on, nullptr, 0, 0, 0}, {tg, nullptr, 2, 1, 0}, {tg, nullptr, 2, 2, 0}};
+    const float* t0 = batch->d_taus;
+    const float* t1 = t0 + (long long)B * c.tau_samples_s_tm1;
+    const float* t2 = t1 + (long long)B * c.tau_samples_policy;
+    const float* taus[3] = {t0, t1, t2};
+    DZ_TRY(forward_heads_iqn(l, passes, 3, B, taus, true, stream));
+  } else if (c.kind == DZ_RAINBOW) {
+    Pass passes[3] = {{on, nullptr, 0, 0, 0}, {on, nullptr, 1, 1, 1}, {tg, nullptr, 2, 2, 2}};
+    DZ_TRY(forward_heads_rainbow(l, passes, 3, B, batch->d_noise, stream));
+  } else {
+    Pass passes[3];
+    int np = 0;
+    passes[np++] = Pass{on, nullptr, 0, 0, 0};
+    if (needs_online_st) passes[np++] = Pass{on, nullptr, 1, 1, 0};
+    passes[np++] = Pass{tg, nullptr, 2, 2, 0};
+    DZ_TRY(forward_heads_plain(l, passes, np, B, stream));
+  }
+
+  // ---- loss + gradient wrt the pass-0 head outputs
+  LossArgs L;
+  memset(&L, 0, sizeof(L));
+  L.kind = c.kind; L.B = B; L.A = c.num_actions; L.atoms = c.num_atoms;
+  L.out0 = l->out[0]; L.out1 = l->out[1]; L.out2 = l->out[2];
+  L.adv0 = l->out[0]; L.val0 = l->outv[0]; L.adv1 = l->out[1]; L.val1 = l->outv[1]; L.adv2 = l->out[2]; L.val2 = l->outv[2];
+  L.a = batch->d_a_tm1; L.r = batch->d_r_t; L.disc = batch->d_discount_t; L.w = batch->d_weights; L.taus0 = batch->d_taus;
+  L.vmax = c.vmax; L.bound = c.grad_error_bound; L.kappa = c.huber_param;
+  L.dout = l->dout; L.dadv = l->dout; L.dval = l->doutv;
+  L.per_example = out->d_per_example; L.loss_terms = l->loss_terms;
+  L.priorities = (c.kind == DZ_RAINBOW || c.kind == DZ_PRIORITIZED) ? out->d_priorities : nullptr;
+  if (c.kind == DZ_DQN || c.kind == DZ_DOUBLE_Q || c.kind == DZ_PRIORITIZED) {
+    DZ_LAUNCH(loss_q_kernel, B, 64, 0, stream, L);
+  } else if (c.kind == DZ_C51 || c.kind == DZ_RAINBOW) {
+    size_t smem = (32 + 4 * c.num_atoms + c.num_actions) * sizeof(float);
+    DZ_LAUNCH(loss_categorical_kernel, B, 128, smem, stream, L);
+  } else {
+    if (c.kind == DZ_QRDQN) { L.N = c.num_quantiles; L.Ksel = c.num_quantiles; L.Nt = c.num_quantiles; }
+    else { L.N = c.tau_samples_s_tm1; L.Ksel = c.tau_samples_policy; L.Nt = c.tau_samples_s_t; }
+    size_t smem = (32 + c.num_actions + L.Nt + 2 * L.N) * sizeof(float);
+    DZ_LAUNCH(loss_quantile_kernel, B, 256, smem, stream, L);
+  }
+  DZ_LAUNCH(loss_mean_kernel, 1, 32, 0, stream, l->loss_terms, B, out->d_loss, max_seen, L.priorities);
+
+  // ---- backward through online(s_tm1)
+  if (c.kind == DZ_RAINBOW) DZ_TRY(backward_rainbow(l, batch->d_noise, stream));
+  else if (c.kind == DZ_IQN) DZ_TRY(backward_iqn(l, stream));
+  else DZ_TRY(backward_plain(l, stream));
+  DZ_TRY(backward_torso(l, batch->d_s_tm1_rows, stream));
+
+  // ---- clip_by_global_norm + adam / rmsprop + apply_updates
+  DZ_TRY(run_optimizer(l, out->d_grad_norm, apply_update != 0, stream));
+  return DZ_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+
+extern "C" {
+
+int dz_learner_plan_query(const dz_learner_config* cfg, dz_learner_plan* out) {
+  DZ_TRY(validate(*cfg));
+  dz_learner tmp;
+  tmp.cfg = *cfg;
+  tmp.lay = make_layout(*cfg);
+  tmp.d = make_dims(*cfg);
+  tmp.B = cfg->batch;
+  out->param_count = tmp.lay.total;
+  out->num_tensors = (int32_t)tmp.lay.t.size();
+  out->opt_state_floats = 2 * tmp.lay.total;
+  out->workspace_bytes = carve(&tmp, nullptr);
+  out->noise_floats = cfg->kind == DZ_RAINBOW ? 3 * noise_stride(*cfg, tmp.d) : 0;
+  out->tau_floats = cfg->kind == DZ_IQN
+                        ? (int64_t)cfg->batch * (cfg->tau_samples_s_tm1 + cfg->tau_samples_policy + cfg->tau_samples_s_t)
+                        : 0;
+  return DZ_OK;
+}
+
+int dz_learner_tensor_info(const dz_learner_config* cfg, int32_t i, char* name64, int64_t* shape4, int32_t* ndim, int64_t* offset) {
+  DZ_TRY(validate(*cfg));
+  Layout L = make_layout(*cfg);
+  if (i < 0 || i >= (int)L.t.size()) return fail(DZ_ERANGE, "tensor index out of range");
+  const TensorInfo& t = L.t[i];
+  snprintf(name64, 64, "%s", t.name.c_str());
+  for (int k = 0; k < 4; ++k) shape4[k] = t.shape[k];
+  *ndim = t.ndim;
+  *offset = t.offset;
+  return DZ_OK;
+}
+
+int dz_learner_create(const dz_learner_config* cfg, const dz_learner_buffers* buf, dz_learner** out) {
+  DZ_TRY(validate(*cfg));
+  if (!buf->d_online || !buf->d_target || !buf->d_grads || !buf->d_opt_state || !buf->d_workspace || !buf->d_counters)
+    return fail(DZ_EINVAL, "all learner buffers are required");
+  dz_learner* l = new dz_learner();
+  l->cfg = *cfg;
+  l->buf = *buf;
+  l->lay = make_layout(*cfg);
+  l->d = make_dims(*cfg);
+  l->B = cfg->batch;
+  carve(l, static_cast<char*>(buf->d_workspace));
+  cudaError_t e = cudaMemset(l->ticket, 0, 16);
+  if (e != cudaSuccess) { delete l; return fail(DZ_ECUDA, "cudaMemset: %s", cudaGetErrorString(e)); }
+  *out = l;
+  return DZ_OK;
+}
+
+void dz_learner_destroy(dz_learner* l) { delete l; }
+
+int dz_learner_update(dz_learner* l, const dz_batch* batch, const dz_update_outputs* out, int32_t apply_update, void* stream) {
+  return update_impl(l, batch, out, apply_update, nullptr, stream);
+}
+
+int dz_learner_learn(dz_learner* l, const dz_replay_view* replay, int32_t prioritized, const dz_learn_io* io, void* stream) {
+  const int B = l->B;
+  BatchExtras ex{l->rows_sample[0], l->rows_sample[1], l->s_a, l->s_r, l->s_d, prioritized ? l->s_w : nullptr, 1};
+  if (replay->obs_bytes != (int64_t)l->d.H * l->d.W * l->d.C) return fail(DZ_EINVAL, "replay observation size does not match the network");
+  DZ_TRY(launch_sample(replay, prioritized, &io->sample_in, &io->sample_out, B, ex, stream));
+  dz_batch batch;
+  batch.d_s_tm1_rows = l->rows_sample[0];
+  batch.d_s_t_rows = l->rows_sample[1];
+  batch.d_a_tm1 = l->s_a; batch.d_r_t = l->s_r; batch.d_discount_t = l->s_d;
+  batch.d_weights = prioritized ? l->s_w : nullptr;
+  batch.d_taus = io->d_taus; batch.d_noise = io->d_noise;
+  DZ_TRY(update_impl(l, &batch, &io->update_out, 1, io->d_max_seen_priority, stream));
+  if (prioritized) {
+    if (!io->update_out.d_priorities) return fail(DZ_EINVAL, "prioritized learn needs update_out.d_priorities");
+    // replay.update_priorities(ids, priorities)  (rainbow/agent.py:198)
+    DZ_TRY(launch_update_priorities(replay, io->sample_out.d_indices, io->update_out.d_priorities, B, io->priority_exponent,
+                                    replay->capacity, stream));
+  }
+  return DZ_OK;
+}
+
+int dz_learner_generate_randomness(dz_learner* l, uint64_t seed, float* d_taus, float* d_noise, void* stream) {
+  const dz_learner_config& c = l->cfg;
+  if (c.kind == DZ_IQN && d_taus) {
+    long long n = (long long)c.batch * (c.tau_samples_s_tm1 + c.tau_samples_policy + c.tau_samples_s_t);
+    DZ_LAUNCH(randomness_kernel, (unsigned)ceil_div(ceil_div(n, 4), 256), 256, 0, stream, d_taus, n, seed, l->buf.d_counters, 0, 1u);
+  }
+  if (c.kind == DZ_RAINBOW && d_noise) {
+    long long n = 3 * noise_stride(c, l->d);
+    DZ_LAUNCH(randomness_kernel, (unsigned)ceil_div(ceil_div(n, 4), 256), 256, 0, stream, d_noise, n, seed, l->buf.d_counters, 1, 2u);
+  }
+  DZ_LAUNCH(bump_counter_kernel, 1, 1, 0, stream, l->buf.d_counters, 1);
+  return DZ_OK;
+}
+
+int dz_learner_q_values(dz_learner* l, const uint8_t* d_obs, const float* d_taus, const float* d_noise, float* d_q_out, void* stream) {
+  const dz_learner_config& c = l->cfg;
+  const float* on = l->buf.d_online;
+  DZ_LAUNCH(make_row_table_kernel, 1, 32, 0, stream, d_obs, (long long)0, 1, l->rows_act);
+  TorsoJob job{on, l->rows_act, 1};   // use activation set 1 so a pending backward's set-0 buffers stay intact
+  DZ_TRY(forward_torso(l, &job, 1, 1, stream));
+  Pass pass{on, nullptr, 1, 1, 0};
+  int nq = 1;
+  if (c.kind == DZ_IQN) {
+    if (!d_taus) return fail(DZ_EINVAL, "iqn q_values needs taus[tau_samples_policy]");
+    const float* taus[1] = {d_taus};
+    DZ_TRY(forward_heads_iqn(l, &pass, 1, 1, taus, false, stream));
+    nq = c.tau_samples_policy;
+  } else if (c.kind == DZ_RAINBOW) {
+    if (!d_noise) return fail(DZ_EINVAL, "rainbow q_values needs one apply of noise");
+    DZ_TRY(forward_heads_rainbow(l, &pass, 1, 1, d_noise, stream));
+  } else {
+    DZ_TRY(forward_heads_plain(l, &pass, 1, 1, stream));
+    nq = c.num_quantiles;
+  }
+  size_t smem = (32 + c.num_atoms + 8) * sizeof(float);
+  DZ_LAUNCH(q_values_kernel, 1, 128, smem, stream, c.kind, c.num_actions, c.num_atoms, nq, c.vmax, l->out[1], l->out[1], l->outv[1], d_q_out);
+  return DZ_OK;
+}
+
+int dz_learner_sync_target(dz_learner* l, void* stream) {
+  DZ_CUDA_OK(cudaMemcpyAsync(l->buf.d_target, l->buf.d_online, l->lay.total * sizeof(float), cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)stream));
+  return DZ_OK;
+}
+
+}  // extern "C"

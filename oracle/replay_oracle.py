@@ -693,7 +693,7 @@ def _mix64(x):
   return x
 
 
-def synthetic_rows(seed, rows, obs_bytes, num_actions):
+def synthetic_rows(seed, rows, obs_bytes, num_actions, discount=0.99):
   """Contents of synthetic transitions `rows` (array of ids), matching the CUDA
   kernel `dz_replay_fill_synthetic` bit for bit (SURVEY §8(d) synthetic inputs).
 
@@ -717,5 +717,5 @@ def synthetic_rows(seed, rows, obs_bytes, num_actions):
     r = np.where(u < 0.05, -1.0, np.where(u < 0.95, 0.0, 1.0))
     h3 = _mix64(base + np.uint64(0xD1B54A32D192ED03) + rows * np.uint64(4) + np.uint64(2))
     u3 = (h3 >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
-    d = np.where(u3 < 0.99, 0.99, 0.0)
+    d = np.where(u3 < 0.99, discount, 0.0)
   return obs, a, r, d
