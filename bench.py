@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Benchmark of the dqn_zoo hot path (replay sample -> learner update -> priority write-back).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--agent rainbow|dqn|c51|iqn|...]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+      bench.py --gpus N --steps K --warmup W
+
+Prints ONE JSON line (rank 0).  Metric = BASELINE.json's: learner grad-steps/s (sampled
+transitions/s = x batch) on a synthetic 84x84x4 uint8 replay of 1M transitions, batch 32.
+`value`  : inputs resident in HBM (pre-uploaded RandomState draws), CUDA-graph step, CUDA events.
+`e2e`    : the public agent.learn() call: host RandomState draws -> pinned -> H2D every step and an
+           asynchronous D2H of the step's loss every step.
+`roofline`: the dominant kernel of the step, timed with CUDA events on its stream (dz_profile_*).
+`cpu_baseline` / `--impl reference`: the oracle PORT of the reference algorithm on the host cores
+(JAX is not installable here or on the GPU box; see oracle/cpu_reference.py).
+"""
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+AGENT_SETUP = {
+    # kind: (prioritized, priority_exponent, n_step, target_period_in_learner_steps)
+    'dqn': (False, 0.0, 1, 40000 // 16), 'double_q': (False, 0.0, 1, 120000 // 16),
+    'prioritized': (True, 0.6, 1, 120000 // 16), 'c51': (False, 0.0, 1, 40000 // 16),
+    'qrdqn': (False, 0.0, 1, 40000 // 16), 'rainbow': (True, 0.5, 3, 32000 // 16), 'iqn': (False, 0.0, 1, 40000 // 16),
+}
+# learner FLOPs per step, B*F_fwd*(n_fwd+2), SURVEY §8(a) (A = 6)
+GFLOP_PER_STEP = {'dqn': 2.39, 'double_q': 2.99, 'prioritized': 2.99, 'c51': 2.43, 'qrdqn': 2.55, 'rainbow': 4.65, 'iqn': 39.5}
+
+
+def parse():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=2000)
+  ap.add_argument('--warmup', type=int, default=200)
+  ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--agent', default='rainbow', choices=sorted(AGENT_SETUP))
+  ap.add_argument('--capacity', type=int, default=1000000)
+  ap.add_argument('--batch', type=int, default=32)
+  ap.add_argument('--seed', type=int, default=1)
+  ap.add_argument('--no-graph', action='store_true')
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--cpu-steps', type=int, default=40)
+  return ap.parse_args()
+
+
+def workload_name(args):
+  pri, alpha, n, _ = AGENT_SETUP[args.agent]
+  rep = 'per_alpha%g' % alpha if pri else 'uniform'
+  return '%s_%s_nstep%d_cap%d_b%d_84x84x4' % (args.agent, rep, n, args.capacity, args.batch)
+
+
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+  def __init__(self, index):
+    self.rows, self.proc, self.index = [], None, index
+
+  def start(self):
+    q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+    try:
+      self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '100',
+                                    '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._pump, daemon=True)
+      self.thread.start()
+    except Exception:
+      self.proc = None
+
+  def _pump(self):
+    for line in self.proc.stdout:
+      self.rows.append(line.strip().split(', '))
+
+  def stop(self):
+    if self.proc is None:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+    time.sleep(0.15)
+    self.proc.terminate()
+    sm, mx, reasons = [], [], set()
+    for r in self.rows:
+      try:
+        sm.append(float(r[1])); mx.append(float(r[2]))
+        for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
+          if v.strip().lower().startswith('active'):
+            reasons.add(name)
+      except Exception:
+        pass
+    return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+            'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def measured_peaks():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(path):
+    with open(path) as f:
+      p = json.load(f)
+    return p.get('hbm_gbs', 6650.0), p.get('bf16_tflops', 1590.0), 'measured (MEASURED_PEAKS.json)'
+  return 6650.0, 1590.0, 'fallback (B200_PROFILING.md)'
+
+
+def reference_arm(args, rank, world):
+  """The oracle PORT of the reference algorithm on the host cores (rank 0 only)."""
+  if rank != 0:
+    return
+  from oracle import cpu_reference
+  steps = max(1, args.steps)
+  res = cpu_reference.run(args.agent, capacity=args.capacity, batch=args.batch, steps=steps, warmup=min(args.warmup, 3),
+                          seed=args.seed, budget_s=120.0)
+  value = res['steps_per_s']
+  sample = ('%d learner steps (replay.sample + update + update_priorities) of %s; replay %.2f ms + learner %.2f ms per '
+            'step; observations reference a pool of 512 synthetic frames' % (res['steps'], workload_name(args),
+                                                                             res['replay_ms'], res['learner_ms']))
+  line = {
+      'impl': 'reference', 'metric': 'learner_grad_steps_per_sec', 'value': value, 'unit': 'grad-steps/s',
+      'sampled_transitions_per_sec': value * args.batch, 'n_gpus': args.gpus, 'steps': res['steps'],
+      'warmup': min(args.warmup, 3), 'ms_per_step': 1e3 / value, 'higher_is_better': True, 'scaling': 'weak',
+      'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': workload_name(args), 'note': 'oracle port (numpy replay + torch-CPU float32 learner); JAX CPU '
+                 'path not installable'},
+      'cpu_baseline': {'value': value, 'unit': 'grad-steps/s', 'cores': res['cores'], 'kind': 'port', 'sample': sample},
+      'e2e': {'value': value, 'unit': 'grad-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+      'gpu_launches': 0,
+  }
+  print(json.dumps(line), flush=True)
+
+
+def build_agent(args, rank, device):
+  from dqn_zoo_b200 import agent as agent_lib
+  from dqn_zoo_b200 import learner as learner_lib
+  from dqn_zoo_b200 import parts
+  from dqn_zoo_b200 import replay as replay_lib
+  pri, alpha, n_step, _ = AGENT_SETUP[args.agent]
+  kind = args.agent
+  seed = args.seed + rank
+  rs = np.random.RandomState(seed)
+  structure = replay_lib.Transition(None, None, None, None, None)
+  if pri:
+    sched = parts.LinearSchedule(begin_t=int(0.02 * args.capacity), end_t=200 * 250000, begin_value=0.4, end_value=1.0)
+    rep = replay_lib.PrioritizedTransitionReplay(args.capacity, structure, alpha, sched, 1e-3, True, rs)
+  else:
+    rep = replay_lib.TransitionReplay(args.capacity, structure, rs)
+  replay_lib.bulk_fill_synthetic(rep, (84, 84, 4), seed, 6, discount=0.99 ** n_step)
+  net = learner_lib.NetworkSpec(kind, 6)
+  acc = replay_lib.NStepTransitionAccumulator(n_step)
+  common = dict(preprocessor=lambda ts: ts, sample_network_input=np.zeros((84, 84, 4), np.uint8), network=net,
+                optimizer=None, transition_accumulator=acc, replay=rep, batch_size=args.batch,
+                min_replay_capacity_fraction=0.02, learn_period=16, target_network_update_period=32000, rng_key=[0, seed],
+                use_cuda_graph=not args.no_graph)
+  eps = lambda t: 0.01
+  if kind == 'rainbow':
+    ag = agent_lib.Rainbow(support=np.linspace(-10, 10, 51), **common)
+  elif kind == 'c51':
+    ag = agent_lib.C51(support=np.linspace(-10, 10, 51), exploration_epsilon=eps, **common)
+  elif kind == 'qrdqn':
+    ag = agent_lib.QrDqn(quantiles=(np.arange(201) + 0.5) / 201, exploration_epsilon=eps, huber_param=1.0, **common)
+  elif kind == 'iqn':
+    ag = agent_lib.Iqn(exploration_epsilon=eps, huber_param=1.0, tau_samples_policy=64, tau_samples_s_tm1=64,
+                       tau_samples_s_t=64, **common)
+  else:
+    ag = agent_lib.AGENTS[kind](exploration_epsilon=eps, grad_error_bound=1.0 / 32, **common)
+  return ag, rep
+
+
+def main():
+  args = parse()
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  if args.impl == 'reference':
+    reference_arm(args, rank, world)
+    return
+  if not torch.cuda.is_available():
+    raise SystemExit('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
+  torch.cuda.set_device(local_rank)
+  device = torch.device('cuda', local_rank)
+  dist = None
+  if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group('nccl', device_id=device)
+  from dqn_zoo_b200 import _lib
+
+  ag, rep = build_agent(args, rank, device)
+  L = ag.learner
+  K, W, B = args.steps, max(args.warmup, 3), args.batch
+  target_period = AGENT_SETUP[args.agent][3]
+
+  def sync_target():
+    # BASELINE configs[4]: periodic online->target parameter broadcast over NCCL/NVLink.  Root 0's
+    # online net becomes every shard's target (shared-target reading); at N=1 it is the
+    # reference's plain target <- online copy.
+    L.sync_target()
+    if dist is not None:
+      dist.broadcast(L.target, src=0)
+
+  def barrier():
+    if dist is not None:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  # ---- (1) value: draws resident in HBM ---------------------------------------------------------
+  draws = np.stack([ag.host_draws() for _ in range(W + K)])
+  d_draws = torch.as_tensor(draws, device=device)
+  for i in range(W):
+    ag.learn_from_device_draws(d_draws[i])
+  barrier()
+  launches_before = _lib.lib.dz_launch_count()
+  clocks = ClockSampler(local_rank)
+  clocks.start()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  e0.record()
+  for i in range(K):
+    ag.learn_from_device_draws(d_draws[W + i])
+    if (i + 1) % target_period == 0:
+      sync_target()
+  e1.record()
+  barrier()
+  clk = clocks.stop()
+  ms = e0.elapsed_time(e1)
+  t = torch.tensor([ms], dtype=torch.float64, device=device)
+  if dist is not None:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  ms_max = float(t.item())
+  value = world * K / (ms_max / 1e3)
+  ag.check_device_flags()
+
+  # ---- (2) e2e: public learn() with host draws + H2D + D2H of the loss every step ---------------
+  loss_host = torch.zeros(K, dtype=torch.float32).pin_memory()
+  for i in range(3):
+    ag.learn()
+  barrier()
+  e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  t_host0 = time.perf_counter()
+  e2.record()
+  for i in range(K):
+    ag.learn()
+    loss_host[i:i + 1].copy_(L.loss, non_blocking=True)
+    if (i + 1) % target_period == 0:
+      sync_target()
+  e3.record()
+  barrier()
+  t_host = time.perf_counter() - t_host0
+  ms_e2e = max(e2.elapsed_time(e3), 1e3 * t_host)
+  t = torch.tensor([ms_e2e], dtype=torch.float64, device=device)
+  if dist is not None:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  e2e_value = world * K / (float(t.item()) / 1e3)
+  assert np.isfinite(loss_host.numpy()).all(), 'non-finite loss in the e2e run'
+  ag.check_device_flags()
+
+  # ---- (3) launches per step + per-kernel timing (outside every timed region) --------------------
+  ag._use_graph = False
+  c0 = _lib.lib.dz_launch_count()
+  ag.learn()
+  torch.cuda.synchronize()
+  launches_per_step = int(_lib.lib.dz_launch_count() - c0)
+  prof_steps = 50
+  _lib.call('dz_profile_begin')
+  for i in range(prof_steps):
+    ag.learn()
+  buf = C.create_string_buffer(1 << 16)
+  _lib.call('dz_profile_end', buf, len(buf))
+  prof = json.loads(buf.value.decode())
+  total_ms = sum(v[1] for v in prof.values())
+  top = max(prof.items(), key=lambda kv: kv[1][1])
+  per_launch_us = {k: 1e3 * v[1] / v[0] for k, v in prof.items()}
+  share = {k: round(v[1] / total_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}
+
+  hbm_peak, tf_peak, peak_src = measured_peaks()
+  # Dominant-kernel roofline.  Algorithmic bytes per launch of each candidate:
+  P = L.plan.param_count
+  alg_bytes = {
+      # noisy fc1 (rainbow): 2 streams x (mu.w + sigma.w) x {online, target} weights read once + 3 x feat reads
+      'noisy1_fwd': 2 * 2 * 2 * 3136 * 512 * 4 + 3 * B * 3136 * 4,
+      'noisy1_wgrad': 2 * 2 * 3136 * 512 * 4 + B * (3136 + 1024) * 4,
+      'noisy1_dgrad': 2 * 2 * 3136 * 512 * 4 + B * (3136 + 1024) * 4 * 2,
+      'fc1_fwd': 2 * 3136 * 512 * 4 + 3 * B * 3136 * 4,
+      'fc1_wgrad': 3136 * 512 * 4 + B * (3136 + 512) * 4,
+      'fc1_dgrad': 3136 * 512 * 4 + B * (3136 + 512) * 4,
+      'optimizer_kernel': 7 * 4 * P,
+      'grad_norm_kernel': 4 * P,
+      'conv1_fwd': (3 if args.agent in ('rainbow', 'double_q', 'prioritized') else 2) * B * (28224 + 20 * 20 * 32 * 4),
+  }
+  name = top[0]
+  dur_s = 1e-3 * top[1][1] / top[1][0]
+  if name in alg_bytes:
+    achieved = alg_bytes[name] / dur_s / 1e9
+    roofline = {'kernel': name, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
+                'frac': achieved / hbm_peak, 'traffic': None, 'alg_bytes_per_launch': alg_bytes[name],
+                'avg_launch_us': 1e6 * dur_s, 'peak_source': peak_src}
+  else:
+    flops = GFLOP_PER_STEP[args.agent] * 1e9
+    achieved = flops / (1e-3 * total_ms / prof_steps) / 1e12
+    roofline = {'kernel': name, 'bound': 'tensor', 'achieved': achieved, 'peak': tf_peak, 'unit': 'TFLOP/s',
+                'frac': achieved / tf_peak, 'traffic': None, 'avg_launch_us': 1e6 * dur_s, 'peak_source': peak_src,
+                'note': 'whole-step algorithmic FLOPs over summed kernel time (fp32 SIMT path, no tensor cores yet)'}
+  roofline['kernel_time_share'] = share
+  roofline['sample_gather'] = {
+      'alg_bytes_per_step': 2 * B * 28224 + 12 * B + (20480 if AGENT_SETUP[args.agent][0] else 0),
+      'note': 'gather is fused into conv1_fwd/conv1_wgrad operand loads; sampler kernel avg us = %.2f'
+              % per_launch_us.get('per_sample_kernel', per_launch_us.get('uniform_sample_kernel', float('nan')))}
+
+  # ---- (4) CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------
+  cpu = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    from oracle import cpu_reference
+    res = cpu_reference.run(args.agent, capacity=args.capacity, batch=B, steps=args.cpu_steps, warmup=2, seed=args.seed,
+                            budget_s=25.0)
+    cpu = {'value': res['steps_per_s'], 'unit': 'grad-steps/s', 'cores': res['cores'], 'kind': 'port',
+           'sample': '%d learner steps of the same workload: numpy replay %.2f ms + torch-CPU f32 learner %.2f ms per step'
+                     % (res['steps'], res['replay_ms'], res['learner_ms'])}
+
+  if rank == 0:
+    stage_bytes = (3 * B + 4) * 8
+    line = {
+        'metric': 'learner_grad_steps_per_sec', 'value': value, 'unit': 'grad-steps/s',
+        'sampled_transitions_per_sec': value * B, 'n_gpus': world, 'steps': K, 'warmup': W,
+        'ms_per_step': ms_max / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32 (f64 sum tree)', 'data': 'synthetic',
+        'config': {'workload': workload_name(args), 'agent': args.agent, 'replay_capacity': args.capacity, 'batch': B,
+                   'replay_bytes_per_gpu': int(rep._store.obs.numel()), 'cuda_graph': not args.no_graph,
+                   'l2': 'inputs larger than L2: 56.4 GB replay store sampled at random rows; the %.1f MB of '
+                         'parameters+optimizer state stay L2-resident as in steady-state training' % (7 * 4 * P / 1e6),
+                   'multi_gpu': 'independent replay+learner shard per rank; NCCL broadcast of the target blob every %d '
+                                'learner steps' % target_period,
+                   'seed': args.seed},
+        'clocks': clk,
+        'e2e': {'value': e2e_value, 'unit': 'grad-steps/s', 'h2d_bytes_per_step': stage_bytes, 'd2h_bytes_per_step': 4,
+                'note': 'agent.learn(): host RandomState draws -> pinned -> H2D; async D2H of the loss each step'},
+        'gpu_launches': launches_per_step * K,
+        'gpu_launches_per_step': launches_per_step,
+        'roofline': roofline,
+        'learner_gflop_per_step': GFLOP_PER_STEP[args.agent],
+        'learner_tflops_achieved': GFLOP_PER_STEP[args.agent] * value / world / 1e3,
+        'cpu_baseline': cpu,
+    }
+    print(json.dumps(line), flush=True)
+  if dist is not None:
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+  main()

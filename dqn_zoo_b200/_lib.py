@@ -79,6 +79,8 @@ _SIGNATURES = {
     'dz_last_error': (C.c_char_p, []),
     'dz_build_info': (C.c_char_p, []),
     'dz_launch_count': (i64, []),
+    'dz_profile_begin': (i32, []),
+    'dz_profile_end': (i32, [C.c_char_p, i64]),
     'dz_sumtree_rebuild': (i32, [vp, i64, i64, vp]),
     'dz_sumtree_set': (i32, [vp, i64, i64, vp, vp, i64, vp, vp]),
     'dz_sumtree_query': (i32, [vp, i64, vp, i64, vp, vp, vp]),

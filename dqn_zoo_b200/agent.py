@@ -75,6 +75,7 @@ class _DeviceAgent(parts.Agent):
     self._statistics = {'state_value': np.nan}
     self._use_graph = use_cuda_graph
     self._graph = None
+    self._graph_key = None
     self._io = None
     self._obs_dev = torch.zeros(int(np.prod(network.obs_shape)), dtype=torch.uint8, device=self._learner.device)
     B = batch_size
@@ -210,31 +211,48 @@ class _DeviceAgent(parts.Agent):
 
   def _learn(self) -> None:
     """rainbow/agent.py:181-198 as one enqueue."""
-    L = self._learner
-    if self.PRIORITIZED:
-      self._replay._distribution.flush()
-    view = self._replay.device_view()
     slot = self._draws()
     self._stage_dev.copy_(slot, non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()
     self._ring_events[self._ring_pos] = ev
     self._ring_pos = (self._ring_pos + 1) % len(self._ring)
+    self._launch()
+
+  def learn(self) -> None:
+    """Public alias of one learner step (`_learn`): host RNG draws -> H2D -> fused device step."""
+    self._learn()
+
+  def learn_from_device_draws(self, draws: torch.Tensor) -> None:
+    """One learner step whose sampling draws are already in device memory (`draws` = float64
+    [3B+4] in the staging layout).  Used by bench.py for the inputs-resident-in-HBM number."""
+    self._stage_dev.copy_(draws, non_blocking=True)
+    self._launch()
+
+  def host_draws(self) -> np.ndarray:
+    """The staging record for the next learner step (consumes the replay's RandomState)."""
+    return self._draws().numpy().copy()
+
+  def _launch(self) -> None:
+    L = self._learner
+    if self.PRIORITIZED:
+      self._replay._distribution.flush()
+    self._view = self._replay.device_view()
+    key = bytes(self._view)
+    if self._graph is not None and key != self._graph_key:
+      self._graph = None                     # a device array moved (growth / set_state): recapture
+    self._graph_key = key
     if self._io is None:
       alpha = self._replay._distribution._priority_exponent if self.PRIORITIZED else 1.0
       self._io = L.make_learn_io(self._stage_dev, self.PRIORITIZED, alpha)
-      self._view = view
-    self._view = view
     if self._use_graph:
       if self._graph is None:
-        self._enqueue()                      # warm-up outside capture
+        self._enqueue()                      # first step runs eagerly (also the warm-up for capture)
         torch.cuda.synchronize()
-        self._capture_view = view
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
           self._enqueue()
-        self._graph = g
-        # the warm-up already performed this step's update: do not replay it twice
+        self._graph = g                      # capture does not execute: nothing was applied twice
       else:
         self._graph.replay()
     else:

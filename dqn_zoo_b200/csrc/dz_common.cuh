@@ -28,14 +28,23 @@ inline int fail(int code, const char* fmt, const char* a = "", const char* b = "
     if (_e != cudaSuccess) return dz::fail(DZ_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
 
+// Optional per-launch CUDA-event timing (dz_profile_begin/end): used by bench.py to time the
+// dominant kernel on its own stream.  Off in every timed run.
+extern bool g_profile;
+void profile_mark(const char* name, void* stream, bool begin);
+
 // Every kernel launch goes through this so bench.py can report `gpu_launches`.
-#define DZ_LAUNCH(kernel, grid, block, smem, stream, ...)                                    \
+#define DZ_LAUNCH_NAMED(name, kernel, grid, block, smem, stream, ...)                        \
   do {                                                                                       \
+    if (dz::g_profile) dz::profile_mark(name, stream, true);                                 \
     kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__);                \
+    if (dz::g_profile) dz::profile_mark(name, stream, false);                                \
     dz::g_launches.fetch_add(1, std::memory_order_relaxed);                                  \
     cudaError_t _e = cudaGetLastError();                                                     \
-    if (_e != cudaSuccess) return dz::fail(DZ_ECUDA, "launch %s: %s", #kernel, cudaGetErrorString(_e)); \
+    if (_e != cudaSuccess) return dz::fail(DZ_ECUDA, "launch %s: %s", name, cudaGetErrorString(_e)); \
   } while (0)
+#define DZ_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  DZ_LAUNCH_NAMED(#kernel, kernel, grid, block, smem, stream, __VA_ARGS__)
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

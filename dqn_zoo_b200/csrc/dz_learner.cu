@@ -814,8 +814,8 @@ void set_conv(GemmProblem& p, int mode, const void* A, int nimg, int H, int W, i
 }
 
 template <typename KernelT>
-int launch_batch(KernelT kernel, const GemmBatch& gb, dim3 grid, int threads, void* stream) {
-  DZ_LAUNCH(kernel, grid, threads, 0, stream, gb);
+int launch_batch(const char* tag, KernelT kernel, const GemmBatch& gb, dim3 grid, int threads, void* stream) {
+  DZ_LAUNCH_NAMED(tag, kernel, grid, threads, 0, stream, gb);
   return DZ_OK;
 }
 
@@ -823,7 +823,7 @@ int launch_batch(KernelT kernel, const GemmBatch& gb, dim3 grid, int threads, vo
 
 // ---- NN launch helpers (tile shapes chosen by M / N) -------------------------------------------
 
-int run_nn(GemmBatch& gb, bool dual, void* stream) {
+int run_nn(const char* tag, GemmBatch& gb, bool dual, void* stream) {
   int maxM = 0, maxN = 0, maxS = 1;
   for (int i = 0; i < gb.n; ++i) {
     maxM = gb.p[i].M > maxM ? gb.p[i].M : maxM;
@@ -832,19 +832,19 @@ int run_nn(GemmBatch& gb, bool dual, void* stream) {
   }
   if (maxM <= 32) {
     dim3 grid((unsigned)ceil_div(maxN, 64), (unsigned)(ceil_div(maxM, 32) * maxS), gb.n);
-    if (dual) return launch_batch(gemm_nn_kernel<32, 64, 16, 2, 4, true>, gb, grid, 256, stream);
-    return launch_batch(gemm_nn_kernel<32, 64, 16, 2, 4, false>, gb, grid, 256, stream);
+    if (dual) return launch_batch(tag, gemm_nn_kernel<32, 64, 16, 2, 4, true>, gb, grid, 256, stream);
+    return launch_batch(tag, gemm_nn_kernel<32, 64, 16, 2, 4, false>, gb, grid, 256, stream);
   }
   if (maxN <= 32 && !dual) {
     dim3 grid(1, (unsigned)(ceil_div(maxM, 128) * maxS), gb.n);
-    return launch_batch(gemm_nn_kernel<128, 32, 16, 4, 4, false>, gb, grid, 256, stream);
+    return launch_batch(tag, gemm_nn_kernel<128, 32, 16, 4, 4, false>, gb, grid, 256, stream);
   }
   dim3 grid((unsigned)ceil_div(maxN, 64), (unsigned)(ceil_div(maxM, 64) * maxS), gb.n);
-  if (dual) return launch_batch(gemm_nn_kernel<64, 64, 16, 4, 4, true>, gb, grid, 256, stream);
-  return launch_batch(gemm_nn_kernel<64, 64, 16, 4, 4, false>, gb, grid, 256, stream);
+  if (dual) return launch_batch(tag, gemm_nn_kernel<64, 64, 16, 4, 4, true>, gb, grid, 256, stream);
+  return launch_batch(tag, gemm_nn_kernel<64, 64, 16, 4, 4, false>, gb, grid, 256, stream);
 }
 
-int run_tn(GemmBatch& gb, void* stream) {
+int run_tn(const char* tag, GemmBatch& gb, void* stream) {
   int maxK = 0, maxN = 0, maxS = 1;
   for (int i = 0; i < gb.n; ++i) {
     int kext = gb.p[i].K + ((gb.p[i].Cb || gb.p[i].Cb2) ? 1 : 0);
@@ -854,13 +854,13 @@ int run_tn(GemmBatch& gb, void* stream) {
   }
   if (maxN <= 32) {
     dim3 grid(1, (unsigned)(ceil_div(maxK, 64) * maxS), gb.n);
-    return launch_batch(gemm_tn_kernel<64, 32, 16, 4, 2>, gb, grid, 256, stream);
+    return launch_batch(tag, gemm_tn_kernel<64, 32, 16, 4, 2>, gb, grid, 256, stream);
   }
   dim3 grid((unsigned)ceil_div(maxN, 64), (unsigned)(ceil_div(maxK, 64) * maxS), gb.n);
-  return launch_batch(gemm_tn_kernel<64, 64, 16, 4, 4>, gb, grid, 256, stream);
+  return launch_batch(tag, gemm_tn_kernel<64, 64, 16, 4, 4>, gb, grid, 256, stream);
 }
 
-int run_nt(GemmBatch& gb, bool dual, void* stream) {
+int run_nt(const char* tag, GemmBatch& gb, bool dual, void* stream) {
   int maxM = 0, maxK = 0;
   for (int i = 0; i < gb.n; ++i) {
     maxM = gb.p[i].M > maxM ? gb.p[i].M : maxM;
@@ -868,12 +868,12 @@ int run_nt(GemmBatch& gb, bool dual, void* stream) {
   }
   if (maxM <= 32) {
     dim3 grid((unsigned)ceil_div(maxK, 64), (unsigned)ceil_div(maxM, 32), gb.n);
-    if (dual) return launch_batch(gemm_nt_kernel<32, 64, 16, 2, 4, true>, gb, grid, 256, stream);
-    return launch_batch(gemm_nt_kernel<32, 64, 16, 2, 4, false>, gb, grid, 256, stream);
+    if (dual) return launch_batch(tag, gemm_nt_kernel<32, 64, 16, 2, 4, true>, gb, grid, 256, stream);
+    return launch_batch(tag, gemm_nt_kernel<32, 64, 16, 2, 4, false>, gb, grid, 256, stream);
   }
   dim3 grid((unsigned)ceil_div(maxK, 64), (unsigned)ceil_div(maxM, 64), gb.n);
-  if (dual) return launch_batch(gemm_nt_kernel<64, 64, 16, 4, 4, true>, gb, grid, 256, stream);
-  return launch_batch(gemm_nt_kernel<64, 64, 16, 4, 4, false>, gb, grid, 256, stream);
+  if (dual) return launch_batch(tag, gemm_nt_kernel<64, 64, 16, 4, 4, true>, gb, grid, 256, stream);
+  return launch_batch(tag, gemm_nt_kernel<64, 64, 16, 4, 4, false>, gb, grid, 256, stream);
 }
 
 int finish_nn(const GemmBatch& gb, float* const* outs, bool dual, void* stream) {
@@ -915,7 +915,7 @@ int forward_torso(dz_learner* l, const TorsoJob* jobs, int njobs, int nimg, void
     p.N = 32; p.ldb = 32; p.ldc = 32; p.relu = 1; p.C = l->act1[jobs[i].set];
     gb.p[i] = p;
   }
-  DZ_TRY(run_nn(gb, false, stream));
+  DZ_TRY(run_nn("conv1_fwd", gb, false, stream));
   for (int i = 0; i < njobs; ++i) {   // conv2
     GemmProblem p = zero_problem();
     set_conv(p, A_CONV_F32, l->act1[jobs[i].set], nimg, d.h1, d.w1, 32, 4, 4, 2);
@@ -923,7 +923,7 @@ int forward_torso(dz_learner* l, const TorsoJob* jobs, int njobs, int nimg, void
     p.N = 64; p.ldb = 64; p.ldc = 64; p.relu = 1; p.C = l->act2[jobs[i].set];
     gb.p[i] = p;
   }
-  DZ_TRY(run_nn(gb, false, stream));
+  DZ_TRY(run_nn("conv2_fwd", gb, false, stream));
   for (int i = 0; i < njobs; ++i) {   // conv3
     GemmProblem p = zero_problem();
     set_conv(p, A_CONV_F32, l->act2[jobs[i].set], nimg, d.h2, d.w2, 64, 3, 3, 1);
@@ -931,7 +931,7 @@ int forward_torso(dz_learner* l, const TorsoJob* jobs, int njobs, int nimg, void
     p.N = 64; p.ldb = 64; p.ldc = 64; p.relu = 1; p.C = l->act3[jobs[i].set];
     gb.p[i] = p;
   }
-  DZ_TRY(run_nn(gb, false, stream));
+  DZ_TRY(run_nn("conv3_fwd", gb, false, stream));
   return DZ_OK;
 }
 
@@ -958,7 +958,7 @@ int forward_heads_plain(dz_learner* l, const Pass* passes, int np, int nimg, voi
     }
     gb.p[i] = p;
   }
-  DZ_TRY(run_nn(gb, false, stream));
+  DZ_TRY(run_nn("fc1_fwd", gb, false, stream));
   if (splits > 1) DZ_TRY(finish_nn(gb, outs, false, stream));
   for (int i = 0; i < np; ++i) {
     GemmProblem p = zero_problem();
@@ -968,7 +968,7 @@ int forward_heads_plain(dz_learner* l, const Pass* passes, int np, int nimg, voi
     p.C = l->out[passes[i].head];
     gb.p[i] = p;
   }
-  DZ_TRY(run_nn(gb, false, stream));
+  DZ_TRY(run_nn("head_fwd", gb, false, stream));
   return DZ_OK;
 }
 
@@ -1004,7 +1004,7 @@ int forward_heads_rainbow(dz_learner* l, const Pass* passes, int np, int nimg, c
       gb.p[q] = p;
     }
   }
-  DZ_TRY(run_nn(gb, true, stream));
+  DZ_TRY(run_nn("noisy1_fwd", gb, true, stream));
   if (splits > 1) DZ_TRY(finish_nn(gb, outs, true, stream));
   for (int i = 0; i < np; ++i) {
     NoiseVecs nz = noise_of(c, d, noise, passes[i].apply);
@@ -1021,7 +1021,7 @@ int forward_heads_rainbow(dz_learner* l, const Pass* passes, int np, int nimg, c
       gb.p[2 * i + s] = p;
     }
   }
-  DZ_TRY(run_nn(gb, true, stream));
+  DZ_TRY(run_nn("noisy2_fwd", gb, true, stream));
   return DZ_OK;
 }
 
@@ -1047,7 +1047,7 @@ int forward_heads_iqn(dz_learner* l, const Pass* passes, int np, int nimg, const
     p.C = l->hi[hp]; p.C2 = (keep_E0 && hp == 0) ? l->E0 : nullptr;
     gb.p[i] = p;
   }
-  DZ_TRY(run_nn(gb, false, stream));
+  DZ_TRY(run_nn("iqn_embed_fwd", gb, false, stream));
   for (int i = 0; i < np; ++i) {
     int hp = passes[i].head;
     GemmProblem p = zero_problem();
@@ -1057,7 +1057,7 @@ int forward_heads_iqn(dz_learner* l, const Pass* passes, int np, int nimg, const
     gb.p[i] = p;
   }
   // M can be small when acting (1 x tau_samples_policy rows): same kernel family handles it
-  DZ_TRY(run_nn(gb, false, stream));
+  DZ_TRY(run_nn("iqn_fc1_fwd", gb, false, stream));
   for (int i = 0; i < np; ++i) {
     int hp = passes[i].head;
     GemmProblem p = zero_problem();
@@ -1066,7 +1066,7 @@ int forward_heads_iqn(dz_learner* l, const Pass* passes, int np, int nimg, const
     p.bias = passes[i].params + L.off("head/b"); p.C = l->out[hp];
     gb.p[i] = p;
   }
-  DZ_TRY(run_nn(gb, false, stream));
+  DZ_TRY(run_nn("iqn_head_fwd", gb, false, stream));
   return DZ_OK;
 }
 
@@ -1091,7 +1091,7 @@ int backward_torso(dz_learner* l, const uint8_t* const* rows0, void* stream) {
     int splits = (int)std::min<int64_t>(32, ceil_div(p.M, 64));
     p.splits = splits; p.split_stride = (long long)(p.K + 1) * 64; p.C = l->tn_partial[2];
     gb.n = 1; gb.p[0] = p;
-    DZ_TRY(run_tn(gb, stream));
+    DZ_TRY(run_tn("conv3_wgrad", gb, stream));
     fb.f[fb.n++] = FinishTN{p.C, splits, p.split_stride, p.K, 64, G + L.off("conv3/w"), nullptr, p.Cb, nullptr, nullptr, nullptr};
   }
   // conv3 dgrad: dcol = dpre3 * W3^T ; col2im with ReLU mask of act2
@@ -1100,7 +1100,7 @@ int backward_torso(dz_learner* l, const uint8_t* const* rows0, void* stream) {
     p.A = l->dact3; p.lda = 64; p.M = B * d.h3 * d.w3; p.N = 64; p.K = 576;
     p.B = P + L.off("conv3/w"); p.ldb = 64; p.C = l->dcol; p.ldc = 576;
     gb.n = 1; gb.p[0] = p;
-    DZ_TRY(run_nt(gb, false, stream));
+    DZ_TRY(run_nt("conv3_dgrad", gb, false, stream));
     long long total = (long long)B * d.h2 * d.w2 * 64;
     DZ_LAUNCH(col2im_kernel, (unsigned)ceil_div(total, 256), 256, 0, stream, l->dcol, l->act2[0], l->dact2, B, d.h2, d.w2, 64, 3, 3, 1,
               d.h3, d.w3);
@@ -1114,7 +1114,7 @@ int backward_torso(dz_learner* l, const uint8_t* const* rows0, void* stream) {
     int splits = (int)std::min<int64_t>(32, ceil_div(p.M, 64));
     p.splits = splits; p.split_stride = (long long)(p.K + 1) * 64; p.C = l->tn_partial[1];
     gb.n = 1; gb.p[0] = p;
-    DZ_TRY(run_tn(gb, stream));
+    DZ_TRY(run_tn("conv2_wgrad", gb, stream));
     fb.f[fb.n++] = FinishTN{p.C, splits, p.split_stride, p.K, 64, G + L.off("conv2/w"), nullptr, p.Cb, nullptr, nullptr, nullptr};
   }
   // conv2 dgrad
@@ -1123,7 +1123,7 @@ int backward_torso(dz_learner* l, const uint8_t* const* rows0, void* stream) {
     p.A = l->dact2; p.lda = 64; p.M = B * d.h2 * d.w2; p.N = 64; p.K = 512;
     p.B = P + L.off("conv2/w"); p.ldb = 64; p.C = l->dcol; p.ldc = 512;
     gb.n = 1; gb.p[0] = p;
-    DZ_TRY(run_nt(gb, false, stream));
+    DZ_TRY(run_nt("conv2_dgrad", gb, false, stream));
     long long total = (long long)B * d.h1 * d.w1 * 32;
     DZ_LAUNCH(col2im_kernel, (unsigned)ceil_div(total, 256), 256, 0, stream, l->dcol, l->act1[0], l->dact1, B, d.h1, d.w1, 32, 4, 4, 2,
               d.h2, d.w2);
@@ -1137,7 +1137,7 @@ int backward_torso(dz_learner* l, const uint8_t* const* rows0, void* stream) {
     int splits = (int)std::min<int64_t>(64, ceil_div(p.M, 64));
     p.splits = splits; p.split_stride = (long long)(p.K + 1) * 32; p.C = l->tn_partial[0];
     gb.n = 1; gb.p[0] = p;
-    DZ_TRY(run_tn(gb, stream));
+    DZ_TRY(run_tn("conv1_wgrad", gb, stream));
     fb.f[fb.n++] = FinishTN{p.C, splits, p.split_stride, p.K, 32, G + L.off("conv1/w"), nullptr, p.Cb, nullptr, nullptr, nullptr};
   }
   dim3 grid((unsigned)ceil_div(577 * 64, 256), fb.n);
@@ -1160,7 +1160,7 @@ int backward_plain(dz_learner* l, void* stream) {
     p.B = l->dout; p.N = d.out; p.ldb = d.out; p.ldc = d.out;
     p.C = G + L.off("head/w"); p.Cb = shared ? l->scalars + 8 + kNormBlocks : G + L.off("head/b");
     gb.p[0] = p;
-    DZ_TRY(run_tn(gb, stream));
+    DZ_TRY(run_tn("head_wgrad", gb, stream));
     if (shared) DZ_LAUNCH(sum_to_scalar_kernel, 1, 128, 0, stream, l->scalars + 8 + kNormBlocks, d.out, G + L.off("head/b"));
   }
   {  // dh1 = dout * Wh^T, masked by h1 > 0
@@ -1168,7 +1168,7 @@ int backward_plain(dz_learner* l, void* stream) {
     p.A = l->dout; p.lda = d.out; p.M = B; p.N = d.out; p.K = 512;
     p.B = P + L.off("head/w"); p.ldb = d.out; p.C = l->dh1[0]; p.ldc = 512; p.mask = l->h1[0][0];
     gb.p[0] = p;
-    DZ_TRY(run_nt(gb, false, stream));
+    DZ_TRY(run_nt("head_dgrad", gb, false, stream));
   }
   {  // fc1 wgrad
     GemmProblem p = zero_problem();
@@ -1176,14 +1176,14 @@ int backward_plain(dz_learner* l, void* stream) {
     p.B = l->dh1[0]; p.N = 512; p.ldb = 512; p.ldc = 512;
     p.C = G + L.off("fc1/w"); p.Cb = G + L.off("fc1/b");
     gb.p[0] = p;
-    DZ_TRY(run_tn(gb, stream));
+    DZ_TRY(run_tn("fc1_wgrad", gb, stream));
   }
   {  // dact3 = dh1 * Wf^T, masked by act3 > 0
     GemmProblem p = zero_problem();
     p.A = l->dh1[0]; p.lda = 512; p.M = B; p.N = 512; p.K = d.feat;
     p.B = P + L.off("fc1/w"); p.ldb = 512; p.C = l->dact3; p.ldc = d.feat; p.mask = l->act3[0];
     gb.p[0] = p;
-    DZ_TRY(run_nt(gb, false, stream));
+    DZ_TRY(run_nt("fc1_dgrad", gb, false, stream));
   }
   return DZ_OK;
 }
@@ -1209,7 +1209,7 @@ int backward_rainbow(dz_learner* l, const float* noise, void* stream) {
     p.a_scale = s == 0 ? nz.a2i : nz.v2i; p.c_scale = s == 0 ? nz.a2o : nz.v2o;
     gb.p[s] = p;
   }
-  DZ_TRY(run_tn(gb, stream));
+  DZ_TRY(run_tn("noisy2_wgrad", gb, stream));
   for (int s = 0; s < 2; ++s) {  // dh1_s
     std::string pre = std::string(st[s]) + "2/";
     int n_out = s == 0 ? c.num_actions * c.num_atoms : c.num_atoms;
@@ -1220,7 +1220,7 @@ int backward_rainbow(dz_learner* l, const float* noise, void* stream) {
     p.C = l->dh1[s]; p.ldc = 512; p.mask = l->h1[0][s];
     gb.p[s] = p;
   }
-  DZ_TRY(run_nt(gb, true, stream));
+  DZ_TRY(run_nt("noisy2_dgrad", gb, true, stream));
   for (int s = 0; s < 2; ++s) {  // first noisy layer weight grads
     std::string pre = std::string(st[s]) + "1/";
     GemmProblem p = zero_problem();
@@ -1230,7 +1230,7 @@ int backward_rainbow(dz_learner* l, const float* noise, void* stream) {
     p.a_scale = s == 0 ? nz.a1i : nz.v1i; p.c_scale = s == 0 ? nz.a1o : nz.v1o;
     gb.p[s] = p;
   }
-  DZ_TRY(run_tn(gb, stream));
+  DZ_TRY(run_tn("noisy1_wgrad", gb, stream));
   for (int s = 0; s < 2; ++s) {  // dact3 contributions
     std::string pre = std::string(st[s]) + "1/";
     GemmProblem p = zero_problem();
@@ -1240,7 +1240,7 @@ int backward_rainbow(dz_learner* l, const float* noise, void* stream) {
     p.C = l->dtmp[s]; p.ldc = d.feat;
     gb.p[s] = p;
   }
-  DZ_TRY(run_nt(gb, true, stream));
+  DZ_TRY(run_nt("noisy1_dgrad", gb, true, stream));
   long long n = (long long)B * d.feat;
   DZ_LAUNCH(add_mask_kernel, (unsigned)ceil_div(n, 256), 256, 0, stream, l->dtmp[0], l->dtmp[1], l->act3[0], l->dact3, n);
   return DZ_OK;
@@ -1267,7 +1267,7 @@ int backward_iqn(dz_learner* l, void* stream) {
     int splits = (int)std::min<int64_t>(16, ceil_div(M, 64));
     p.splits = splits; p.split_stride = (long long)513 * d.out; p.C = part_head;
     gb.p[0] = p;
-    DZ_TRY(run_tn(gb, stream));
+    DZ_TRY(run_tn("iqn_head_wgrad", gb, stream));
     fb.f[fb.n++] = FinishTN{p.C, splits, p.split_stride, 512, d.out, G + L.off("head/w"), nullptr, p.Cb, nullptr, nullptr, nullptr};
   }
   {  // dh1
@@ -1275,7 +1275,7 @@ int backward_iqn(dz_learner* l, void* stream) {
     p.A = l->dout; p.lda = d.out; p.M = M; p.N = d.out; p.K = 512;
     p.B = P + L.off("head/w"); p.ldb = d.out; p.C = l->dh1[0]; p.ldc = 512; p.mask = l->h1[0][0];
     gb.p[0] = p;
-    DZ_TRY(run_nt(gb, false, stream));
+    DZ_TRY(run_nt("iqn_head_dgrad", gb, false, stream));
   }
   {  // fc1 wgrad (reduction over M rows, no split: 400 tiles already)
     GemmProblem p = zero_problem();
@@ -1283,14 +1283,14 @@ int backward_iqn(dz_learner* l, void* stream) {
     p.B = l->dh1[0]; p.N = 512; p.ldb = 512; p.ldc = 512;
     p.C = G + L.off("fc1/w"); p.Cb = G + L.off("fc1/b");
     gb.p[0] = p;
-    DZ_TRY(run_tn(gb, stream));
+    DZ_TRY(run_tn("iqn_fc1_wgrad", gb, stream));
   }
   {  // dHI = dh1 * Wf^T
     GemmProblem p = zero_problem();
     p.A = l->dh1[0]; p.lda = 512; p.M = M; p.N = 512; p.K = d.feat;
     p.B = P + L.off("fc1/w"); p.ldb = 512; p.C = l->dhi; p.ldc = d.feat;
     gb.p[0] = p;
-    DZ_TRY(run_nt(gb, false, stream));
+    DZ_TRY(run_nt("iqn_fc1_dgrad", gb, false, stream));
   }
   DZ_LAUNCH(iqn_hadamard_bwd_kernel, (unsigned)ceil_div((long long)B * d.feat, 256), 256, 0, stream, l->dhi, l->E0, l->act3[0],
             l->dact3, B, N, d.feat);
@@ -1302,7 +1302,7 @@ int backward_iqn(dz_learner* l, void* stream) {
     int splits = (int)std::min<int64_t>(16, ceil_div(M, 64));
     p.splits = splits; p.split_stride = (long long)(c.latent_dim + 1) * d.feat; p.C = part_embed;
     gb.p[0] = p;
-    DZ_TRY(run_tn(gb, stream));
+    DZ_TRY(run_tn("iqn_embed_wgrad", gb, stream));
     fb.f[fb.n++] = FinishTN{p.C, splits, p.split_stride, c.latent_dim, d.feat, G + L.off("embed/w"), nullptr, p.Cb, nullptr, nullptr, nullptr};
   }
   long long mx = std::max<long long>((long long)513 * d.out, (long long)(c.latent_dim + 1) * d.feat);

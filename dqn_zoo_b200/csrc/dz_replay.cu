@@ -3,12 +3,33 @@
 // :429-651 (PrioritizedDistribution), :654-768 (PrioritizedTransitionReplay).  All float64
 // arithmetic that feeds an index decision uses explicit round-to-nearest intrinsics so nvcc
 // cannot contract a*b+c into an FMA: results are bit-identical to numpy's.
+#include <map>
+#include <vector>
+
 #include "dz_internal.cuh"
 
 namespace dz {
 
 thread_local std::string g_last_error;
 std::atomic<int64_t> g_launches{0};
+bool g_profile = false;
+
+namespace {
+struct ProfileRec { const char* name; cudaEvent_t a, b; };
+std::vector<ProfileRec> g_profile_recs;
+}  // namespace
+
+void profile_mark(const char* name, void* stream, bool begin) {
+  if (begin) {
+    ProfileRec r{name, nullptr, nullptr};
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, (cudaStream_t)stream);
+    g_profile_recs.push_back(r);
+  } else if (!g_profile_recs.empty()) {
+    cudaEventRecord(g_profile_recs.back().b, (cudaStream_t)stream);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // Sum tree device routines
@@ -424,6 +445,40 @@ extern "C" {
 const char* dz_last_error(void) { return g_last_error.c_str(); }
 const char* dz_build_info(void) { return "dqn_zoo_b200 0.1 sm_100a " __DATE__ " " __TIME__; }
 int64_t dz_launch_count(void) { return g_launches.load(); }
+
+int dz_profile_begin(void) {
+  g_profile_recs.clear();
+  g_profile = true;
+  return DZ_OK;
+}
+
+int dz_profile_end(char* out, int64_t cap) {
+  g_profile = false;
+  DZ_CUDA_OK(cudaDeviceSynchronize());
+  std::map<std::string, std::pair<int64_t, double>> agg;
+  std::vector<std::string> order;
+  for (auto& r : g_profile_recs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+    if (!agg.count(r.name)) order.push_back(r.name);
+    agg[r.name].first += 1;
+    agg[r.name].second += ms;
+  }
+  g_profile_recs.clear();
+  std::string js = "{";
+  for (size_t i = 0; i < order.size(); ++i) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s\"%s\": [%lld, %.6f]", i ? ", " : "", order[i].c_str(), (long long)agg[order[i]].first,
+             agg[order[i]].second);
+    js += buf;
+  }
+  js += "}";
+  if ((int64_t)js.size() + 1 > cap) return fail(DZ_EINVAL, "profile buffer too small");
+  memcpy(out, js.c_str(), js.size() + 1);
+  return DZ_OK;
+}
 
 int dz_sumtree_rebuild(double* d_nodes, int64_t first_leaf, int64_t n_valid, void* stream) {
   if (first_leaf <= 0 || (first_leaf & (first_leaf - 1))) return fail(DZ_EINVAL, "first_leaf must be a power of two");

@@ -750,6 +750,7 @@ class TransitionReplay:
     self._structure = structure
     self._random_state = random_state
     self._distribution = UniformDistribution(random_state=random_state)
+    self._distribution._mirror.ensure(capacity)   # fixed address: captured CUDA graphs keep pointing at it
     self._store = _TransitionStore(capacity)
     self._live_ids = collections.deque()   # ids currently stored, oldest first (keys of the OrderedDict)
     self._t = 0

