@@ -144,7 +144,8 @@ def build_agent(args, rank, device):
   from dqn_zoo_b200 import replay as replay_lib
   pri, alpha, n_step, _ = AGENT_SETUP[args.agent]
   kind = args.agent
-  seed = args.seed + rank
+  from dqn_zoo_b200 import distributed as dz_dist
+  seed = dz_dist.shard_seed(args.seed, rank)
   rs = np.random.RandomState(seed)
   structure = replay_lib.Transition(None, None, None, None, None)
   if pri:
@@ -197,13 +198,13 @@ def main():
   K, W, B = args.steps, max(args.warmup, 3), args.batch
   target_period = AGENT_SETUP[args.agent][3]
 
+  from dqn_zoo_b200 import distributed as dz_dist
+
   def sync_target():
     # BASELINE configs[4]: periodic online->target parameter broadcast over NCCL/NVLink.  Root 0's
     # online net becomes every shard's target (shared-target reading); at N=1 it is the
     # reference's plain target <- online copy.
-    L.sync_target()
-    if dist is not None:
-      dist.broadcast(L.target, src=0)
+    dz_dist.broadcast_target(L.online, L.target, dist, src=0)
 
   def barrier():
     if dist is not None:

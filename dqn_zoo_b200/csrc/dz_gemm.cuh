@@ -110,17 +110,29 @@ struct Acc {
   }
 };
 
-// One BK-deep rank update from shared tiles As[BK][BM+PAD], Bs[BK][BN+PAD].
+template <int N>
+__device__ __forceinline__ void lds_vec(const float* p, float* out) {
+  if constexpr (N == 4) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
+  } else if constexpr (N == 2) {
+    float2 t = *reinterpret_cast<const float2*>(p);
+    out[0] = t.x; out[1] = t.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) out[i] = p[i];
+  }
+}
+
+// One BK-deep rank update from shared tiles As[BK][BM+PAD], Bs[BK][BN+PAD] (vectorised LDS).
 template <int BM, int BN, int BK, int TM, int TN, int PAD>
 __device__ __forceinline__ void tile_fma(const float (*As)[BM + PAD], const float (*Bs)[BN + PAD], int ty, int tx,
                                          Acc<TM, TN>& acc) {
 #pragma unroll
   for (int k = 0; k < BK; ++k) {
     float a[TM], b[TN];
-#pragma unroll
-    for (int i = 0; i < TM; ++i) a[i] = As[k][ty * TM + i];
-#pragma unroll
-    for (int j = 0; j < TN; ++j) b[j] = Bs[k][tx * TN + j];
+    lds_vec<TM>(&As[k][ty * TM], a);
+    lds_vec<TN>(&Bs[k][tx * TN], b);
 #pragma unroll
     for (int i = 0; i < TM; ++i)
 #pragma unroll
@@ -129,6 +141,20 @@ __device__ __forceinline__ void tile_fma(const float (*As)[BM + PAD], const floa
 }
 
 constexpr int kPad = 4;
+
+__device__ __forceinline__ float4 ld4_guard(const float* src, int n, int N, bool vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vec && n + 3 < N) return *reinterpret_cast<const float4*>(src);
+  if (n + 0 < N) v.x = src[0];
+  if (n + 1 < N) v.y = src[1];
+  if (n + 2 < N) v.z = src[2];
+  if (n + 3 < N) v.w = src[3];
+  return v;
+}
+
+// All three kernels share one software pipeline: tiles are double buffered in shared memory and the
+// next tile's global loads are issued into registers BEFORE the current tile's FMAs, so HBM/L2
+// latency overlaps the math and there is one __syncthreads per k-step.
 
 // ---------------------------------------------------------------------------------------------
 // NN: C[M,N] = A[M,K] * B[K,N]  (+ dual accumulate for noisy layers, bias / ReLU / Hadamard epilogue)
@@ -146,10 +172,9 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_nn_kernel(const __
   const int per = (kchunks + p.splits - 1) / p.splits;
   const int kc0 = split * per, kc1 = min(kchunks, kc0 + per);
 
-  __shared__ __align__(16) float As[BK][BM + kPad];
-  __shared__ __align__(16) float Bs[BK][BN + kPad];
-  __shared__ __align__(16) float As2[DUAL ? BK : 1][DUAL ? BM + kPad : 1];
-  __shared__ __align__(16) float Bs2[DUAL ? BK : 1][DUAL ? BN + kPad : 1];
+  constexpr int D = DUAL ? 2 : 1;
+  __shared__ __align__(16) float As[2 * D][BK][BM + kPad];   // [buf*D + which]
+  __shared__ __align__(16) float Bs[2 * D][BK][BN + kPad];
 
   const int tid = threadIdx.x, tx = tid % (BN / TN), ty = tid / (BN / TN);
   constexpr int A_VEC = BM * BK / 4, B_VEC = BK * BN / 4;
@@ -166,19 +191,18 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_nn_kernel(const __
   acc.clear();
   if (DUAL) acc2.clear();
 
-  for (int kc = kc0; kc < kc1; ++kc) {
+  float4 ra[A_PER], rs[A_PER], rb[B_PER], rb2[B_PER];
+  auto gload = [&](int kc) {
     const int k0 = kc * BK;
 #pragma unroll
     for (int i = 0; i < A_PER; ++i) {
       int v = tid + i * NT;
       if (v < A_VEC) {
-        int r = v / (BK / 4), kq = (v % (BK / 4)) * 4;
-        float4 a = a_load4(p, rows[i], k0 + kq);
-        As[kq + 0][r] = a.x; As[kq + 1][r] = a.y; As[kq + 2][r] = a.z; As[kq + 3][r] = a.w;
+        int kq = (v % (BK / 4)) * 4;
+        ra[i] = a_load4(p, rows[i], k0 + kq);
         if (DUAL) {
-          float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (k0 + kq < p.K) s = *reinterpret_cast<const float4*>(p.a_scale + k0 + kq);
-          As2[kq + 0][r] = a.x * s.x; As2[kq + 1][r] = a.y * s.y; As2[kq + 2][r] = a.z * s.z; As2[kq + 3][r] = a.w * s.w;
+          rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k0 + kq < p.K) rs[i] = *reinterpret_cast<const float4*>(p.a_scale + k0 + kq);
         }
       }
     }
@@ -188,27 +212,51 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_nn_kernel(const __
       if (v < B_VEC) {
         int kr = v / (BN / 4), nq = (v % (BN / 4)) * 4;
         int k = k0 + kr, n = n0 + nq;
-        float4 b = make_float4(0.f, 0.f, 0.f, 0.f), b2 = b;
+        rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (DUAL) rb2[i] = rb[i];
         if (k < p.K) {
-          const float* src = p.B + (long long)k * p.ldb + n;
-          if (vecB && n + 3 < p.N) {
-            b = *reinterpret_cast<const float4*>(src);
-            if (DUAL) b2 = *reinterpret_cast<const float4*>(p.B2 + (long long)k * p.ldb + n);
-          } else {
-            const float* src2 = DUAL ? p.B2 + (long long)k * p.ldb + n : nullptr;
-            if (n + 0 < p.N) { b.x = src[0]; if (DUAL) b2.x = src2[0]; }
-            if (n + 1 < p.N) { b.y = src[1]; if (DUAL) b2.y = src2[1]; }
-            if (n + 2 < p.N) { b.z = src[2]; if (DUAL) b2.z = src2[2]; }
-            if (n + 3 < p.N) { b.w = src[3]; if (DUAL) b2.w = src2[3]; }
-          }
+          rb[i] = ld4_guard(p.B + (long long)k * p.ldb + n, n, p.N, vecB);
+          if (DUAL) rb2[i] = ld4_guard(p.B2 + (long long)k * p.ldb + n, n, p.N, vecB);
         }
-        *reinterpret_cast<float4*>(&Bs[kr][nq]) = b;
-        if (DUAL) *reinterpret_cast<float4*>(&Bs2[kr][nq]) = b2;
       }
     }
-    __syncthreads();
-    tile_fma<BM, BN, BK, TM, TN, kPad>(As, Bs, ty, tx, acc);
-    if constexpr (DUAL) tile_fma<BM, BN, BK, TM, TN, kPad>(As2, Bs2, ty, tx, acc2);
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < A_PER; ++i) {
+      int v = tid + i * NT;
+      if (v < A_VEC) {
+        int r = v / (BK / 4), kq = (v % (BK / 4)) * 4;
+        float4 a = ra[i];
+        float (*A0)[BM + kPad] = As[buf * D];
+        A0[kq + 0][r] = a.x; A0[kq + 1][r] = a.y; A0[kq + 2][r] = a.z; A0[kq + 3][r] = a.w;
+        if (DUAL) {
+          float4 sc = rs[i];
+          float (*A1)[BM + kPad] = As[buf * D + D - 1];
+          A1[kq + 0][r] = a.x * sc.x; A1[kq + 1][r] = a.y * sc.y; A1[kq + 2][r] = a.z * sc.z; A1[kq + 3][r] = a.w * sc.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < B_PER; ++i) {
+      int v = tid + i * NT;
+      if (v < B_VEC) {
+        int kr = v / (BN / 4), nq = (v % (BN / 4)) * 4;
+        *reinterpret_cast<float4*>(&Bs[buf * D][kr][nq]) = rb[i];
+        if (DUAL) *reinterpret_cast<float4*>(&Bs[buf * D + D - 1][kr][nq]) = rb2[i];
+      }
+    }
+  };
+
+  if (kc0 < kc1) { gload(kc0); sstore(0); }
+  __syncthreads();
+  for (int kc = kc0; kc < kc1; ++kc) {
+    const int cur = (kc - kc0) & 1;
+    const bool more = kc + 1 < kc1;
+    if (more) gload(kc + 1);
+    tile_fma<BM, BN, BK, TM, TN, kPad>(As[cur * D], Bs[cur * D], ty, tx, acc);
+    if constexpr (DUAL) tile_fma<BM, BN, BK, TM, TN, kPad>(As[cur * D + 1], Bs[cur * D + 1], ty, tx, acc2);
+    if (more) sstore(cur ^ 1);
     __syncthreads();
   }
 
@@ -261,49 +309,66 @@ __global__ void __launch_bounds__((BMK / TM) * (BN / TN)) gemm_tn_kernel(const _
   const int per = (rchunks + p.splits - 1) / p.splits;
   const int rc0 = split * per, rc1 = min(rchunks, rc0 + per);
 
-  __shared__ __align__(16) float As[BR][BMK + kPad];
-  __shared__ __align__(16) float Bs[BR][BN + kPad];
+  __shared__ __align__(16) float As[2][BR][BMK + kPad];
+  __shared__ __align__(16) float Bs[2][BR][BN + kPad];
   const int tid = threadIdx.x, tx = tid % (BN / TN), ty = tid / (BN / TN);
   constexpr int A_VEC = BR * BMK / 4, B_VEC = BR * BN / 4;
+  constexpr int A_PER = (A_VEC + NT - 1) / NT, B_PER = (B_VEC + NT - 1) / NT;
   const bool vecG = (p.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0);
   Acc<TM, TN> acc;
   acc.clear();
-
-  for (int rc = rc0; rc < rc1; ++rc) {
+  float4 ra[A_PER], rb[B_PER];
+  auto gload = [&](int rc) {
     const int r0 = rc * BR;
-    for (int v = tid; v < A_VEC; v += NT) {
-      int rr = v / (BMK / 4), kq = (v % (BMK / 4)) * 4;
-      int m = r0 + rr, k = kk0 + kq;
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < p.M) {
-        if (k < p.K) {
-          ARow row = a_row_base(p, m);
-          a = a_load4(p, row, k);
-        } else if (k == p.K) {
-          a.x = 1.0f;  // bias-gradient row
+#pragma unroll
+    for (int i = 0; i < A_PER; ++i) {
+      int v = tid + i * NT;
+      if (v < A_VEC) {
+        int rr = v / (BMK / 4), kq = (v % (BMK / 4)) * 4;
+        int m = r0 + rr, k = kk0 + kq;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < p.M) {
+          if (k < p.K) {
+            ARow row = a_row_base(p, m);
+            a = a_load4(p, row, k);
+          } else if (k == p.K) {
+            a.x = 1.0f;  // bias-gradient row
+          }
         }
+        ra[i] = a;
       }
-      *reinterpret_cast<float4*>(&As[rr][kq]) = a;
     }
-    for (int v = tid; v < B_VEC; v += NT) {
-      int rr = v / (BN / 4), nq = (v % (BN / 4)) * 4;
-      int m = r0 + rr, n = n0 + nq;
-      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < p.M) {
-        const float* src = p.B + (long long)m * p.ldb + n;
-        if (vecG && n + 3 < p.N) {
-          g = *reinterpret_cast<const float4*>(src);
-        } else {
-          if (n + 0 < p.N) g.x = src[0];
-          if (n + 1 < p.N) g.y = src[1];
-          if (n + 2 < p.N) g.z = src[2];
-          if (n + 3 < p.N) g.w = src[3];
-        }
+#pragma unroll
+    for (int i = 0; i < B_PER; ++i) {
+      int v = tid + i * NT;
+      if (v < B_VEC) {
+        int rr = v / (BN / 4), nq = (v % (BN / 4)) * 4;
+        int m = r0 + rr, n = n0 + nq;
+        rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < p.M) rb[i] = ld4_guard(p.B + (long long)m * p.ldb + n, n, p.N, vecG);
       }
-      *reinterpret_cast<float4*>(&Bs[rr][nq]) = g;
     }
-    __syncthreads();
-    tile_fma<BMK, BN, BR, TM, TN, kPad>(As, Bs, ty, tx, acc);
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < A_PER; ++i) {
+      int v = tid + i * NT;
+      if (v < A_VEC) *reinterpret_cast<float4*>(&As[buf][v / (BMK / 4)][(v % (BMK / 4)) * 4]) = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < B_PER; ++i) {
+      int v = tid + i * NT;
+      if (v < B_VEC) *reinterpret_cast<float4*>(&Bs[buf][v / (BN / 4)][(v % (BN / 4)) * 4]) = rb[i];
+    }
+  };
+  if (rc0 < rc1) { gload(rc0); sstore(0); }
+  __syncthreads();
+  for (int rc = rc0; rc < rc1; ++rc) {
+    const int cur = (rc - rc0) & 1;
+    const bool more = rc + 1 < rc1;
+    if (more) gload(rc + 1);
+    tile_fma<BMK, BN, BR, TM, TN, kPad>(As[cur], Bs[cur], ty, tx, acc);
+    if (more) sstore(cur ^ 1);
     __syncthreads();
   }
 
@@ -333,18 +398,23 @@ __global__ void __launch_bounds__((BMK / TM) * (BN / TN)) gemm_tn_kernel(const _
 
 // ---------------------------------------------------------------------------------------------
 // NT (input gradient): C[M,K] = G[M,N] * B[K,N]^T, optional dual (noisy) term and ReLU mask.
-// grid = (tiles_k, tiles_m, problems)
+// grid = (tiles_k, tiles_m * splits, problems); splits over the reduction dim N: partial s (raw acc,
+// then raw acc2 for DUAL) goes to C + s*split_stride with layout [M][K].
 // ---------------------------------------------------------------------------------------------
 template <int BM, int BNK, int BR, int TM, int TN, bool DUAL>
 __global__ void __launch_bounds__((BM / TM) * (BNK / TN)) gemm_nt_kernel(const __grid_constant__ GemmBatch batch) {
   constexpr int NT = (BM / TM) * (BNK / TN);
   const GemmProblem& p = batch.p[blockIdx.z];
-  const int m0 = blockIdx.y * BM, k0 = blockIdx.x * BNK;
-  if (m0 >= p.M || k0 >= p.K) return;
-  __shared__ __align__(16) float As[BR][BM + kPad];
-  __shared__ __align__(16) float Bs[BR][BNK + kPad];
-  __shared__ __align__(16) float As2[DUAL ? BR : 1][DUAL ? BM + kPad : 1];
-  __shared__ __align__(16) float Bs2[DUAL ? BR : 1][DUAL ? BNK + kPad : 1];
+  const int tiles_m = (p.M + BM - 1) / BM;
+  const int tile_m = blockIdx.y % tiles_m, split = blockIdx.y / tiles_m;
+  const int m0 = tile_m * BM, k0 = blockIdx.x * BNK;
+  if (blockIdx.y >= tiles_m * p.splits || k0 >= p.K) return;
+  const int nchunks = (p.N + BR - 1) / BR;
+  const int per = (nchunks + p.splits - 1) / p.splits;
+  const int nc0 = split * per, nc1 = min(nchunks, nc0 + per);
+  constexpr int D = DUAL ? 2 : 1;
+  __shared__ __align__(16) float As[2 * D][BR][BM + kPad];
+  __shared__ __align__(16) float Bs[2 * D][BR][BNK + kPad];
   const int tid = threadIdx.x, tx = tid % (BNK / TN), ty = tid / (BNK / TN);
   const bool vec = (p.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) && (p.lda % 4 == 0) &&
@@ -354,53 +424,77 @@ __global__ void __launch_bounds__((BM / TM) * (BNK / TN)) gemm_nt_kernel(const _
   acc.clear();
   if (DUAL) acc2.clear();
   constexpr int A_VEC = BM * BR / 4, B_VEC = BNK * BR / 4;
-
-  for (int n0 = 0; n0 < p.N; n0 += BR) {
-    for (int v = tid; v < A_VEC; v += NT) {
-      int r = v / (BR / 4), nq = (v % (BR / 4)) * 4;
-      int m = m0 + r, n = n0 + nq;
-      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < p.M) {
-        const float* src = G + (long long)m * p.lda + n;
-        if (vec && n + 3 < p.N) {
-          g = *reinterpret_cast<const float4*>(src);
-        } else {
-          if (n + 0 < p.N) g.x = src[0];
-          if (n + 1 < p.N) g.y = src[1];
-          if (n + 2 < p.N) g.z = src[2];
-          if (n + 3 < p.N) g.w = src[3];
-        }
-      }
-      As[nq + 0][r] = g.x; As[nq + 1][r] = g.y; As[nq + 2][r] = g.z; As[nq + 3][r] = g.w;
-      if (DUAL) {
-        float s0 = n + 0 < p.N ? p.c_scale[n + 0] : 0.f, s1 = n + 1 < p.N ? p.c_scale[n + 1] : 0.f;
-        float s2 = n + 2 < p.N ? p.c_scale[n + 2] : 0.f, s3 = n + 3 < p.N ? p.c_scale[n + 3] : 0.f;
-        As2[nq + 0][r] = g.x * s0; As2[nq + 1][r] = g.y * s1; As2[nq + 2][r] = g.z * s2; As2[nq + 3][r] = g.w * s3;
+  constexpr int A_PER = (A_VEC + NT - 1) / NT, B_PER = (B_VEC + NT - 1) / NT;
+  float4 ra[A_PER], rs[A_PER], rb[B_PER], rb2[B_PER];
+  auto gload = [&](int nc) {
+    const int n0 = nc * BR;
+#pragma unroll
+    for (int i = 0; i < A_PER; ++i) {
+      int v = tid + i * NT;
+      if (v < A_VEC) {
+        int r = v / (BR / 4), nq = (v % (BR / 4)) * 4;
+        int m = m0 + r, n = n0 + nq;
+        ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < p.M) ra[i] = ld4_guard(G + (long long)m * p.lda + n, n, p.N, vec);
+        if (DUAL) rs[i] = ld4_guard(p.c_scale + n, n, p.N, false);
       }
     }
-    for (int v = tid; v < B_VEC; v += NT) {
-      int kr = v / (BR / 4), nq = (v % (BR / 4)) * 4;
-      int k = k0 + kr, n = n0 + nq;
-      float4 b = make_float4(0.f, 0.f, 0.f, 0.f), b2 = b;
-      if (k < p.K) {
-        const float* src = p.B + (long long)k * p.ldb + n;
-        const float* src2 = DUAL ? p.B2 + (long long)k * p.ldb + n : nullptr;
-        if (vec && n + 3 < p.N) {
-          b = *reinterpret_cast<const float4*>(src);
-          if (DUAL) b2 = *reinterpret_cast<const float4*>(src2);
-        } else {
-          if (n + 0 < p.N) { b.x = src[0]; if (DUAL) b2.x = src2[0]; }
-          if (n + 1 < p.N) { b.y = src[1]; if (DUAL) b2.y = src2[1]; }
-          if (n + 2 < p.N) { b.z = src[2]; if (DUAL) b2.z = src2[2]; }
-          if (n + 3 < p.N) { b.w = src[3]; if (DUAL) b2.w = src2[3]; }
+#pragma unroll
+    for (int i = 0; i < B_PER; ++i) {
+      int v = tid + i * NT;
+      if (v < B_VEC) {
+        int kr = v / (BR / 4), nq = (v % (BR / 4)) * 4;
+        int k = k0 + kr, n = n0 + nq;
+        rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (DUAL) rb2[i] = rb[i];
+        if (k < p.K) {
+          rb[i] = ld4_guard(p.B + (long long)k * p.ldb + n, n, p.N, vec);
+          if (DUAL) rb2[i] = ld4_guard(p.B2 + (long long)k * p.ldb + n, n, p.N, vec);
         }
       }
-      Bs[nq + 0][kr] = b.x; Bs[nq + 1][kr] = b.y; Bs[nq + 2][kr] = b.z; Bs[nq + 3][kr] = b.w;
-      if (DUAL) { Bs2[nq + 0][kr] = b2.x; Bs2[nq + 1][kr] = b2.y; Bs2[nq + 2][kr] = b2.z; Bs2[nq + 3][kr] = b2.w; }
     }
-    __syncthreads();
-    tile_fma<BM, BNK, BR, TM, TN, kPad>(As, Bs, ty, tx, acc);
-    if constexpr (DUAL) tile_fma<BM, BNK, BR, TM, TN, kPad>(As2, Bs2, ty, tx, acc2);
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < A_PER; ++i) {
+      int v = tid + i * NT;
+      if (v < A_VEC) {
+        int r = v / (BR / 4), nq = (v % (BR / 4)) * 4;
+        float4 g = ra[i];
+        float (*A0)[BM + kPad] = As[buf * D];
+        A0[nq + 0][r] = g.x; A0[nq + 1][r] = g.y; A0[nq + 2][r] = g.z; A0[nq + 3][r] = g.w;
+        if (DUAL) {
+          float4 sc = rs[i];
+          float (*A1)[BM + kPad] = As[buf * D + D - 1];
+          A1[nq + 0][r] = g.x * sc.x; A1[nq + 1][r] = g.y * sc.y; A1[nq + 2][r] = g.z * sc.z; A1[nq + 3][r] = g.w * sc.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < B_PER; ++i) {
+      int v = tid + i * NT;
+      if (v < B_VEC) {
+        int kr = v / (BR / 4), nq = (v % (BR / 4)) * 4;
+        float4 b = rb[i];
+        float (*B0)[BNK + kPad] = Bs[buf * D];
+        B0[nq + 0][kr] = b.x; B0[nq + 1][kr] = b.y; B0[nq + 2][kr] = b.z; B0[nq + 3][kr] = b.w;
+        if (DUAL) {
+          float4 b2 = rb2[i];
+          float (*B1)[BNK + kPad] = Bs[buf * D + D - 1];
+          B1[nq + 0][kr] = b2.x; B1[nq + 1][kr] = b2.y; B1[nq + 2][kr] = b2.z; B1[nq + 3][kr] = b2.w;
+        }
+      }
+    }
+  };
+  if (nc0 < nc1) { gload(nc0); sstore(0); }
+  __syncthreads();
+  for (int nc = nc0; nc < nc1; ++nc) {
+    const int cur = (nc - nc0) & 1;
+    const bool more = nc + 1 < nc1;
+    if (more) gload(nc + 1);
+    tile_fma<BM, BNK, BR, TM, TN, kPad>(As[cur * D], Bs[cur * D], ty, tx, acc);
+    if constexpr (DUAL) tile_fma<BM, BNK, BR, TM, TN, kPad>(As[cur * D + 1], Bs[cur * D + 1], ty, tx, acc2);
+    if (more) sstore(cur ^ 1);
     __syncthreads();
   }
 
@@ -412,6 +506,12 @@ __global__ void __launch_bounds__((BM / TM) * (BNK / TN)) gemm_nt_kernel(const _
     for (int j = 0; j < TN; ++j) {
       int k = k0 + tx * TN + j;
       if (k >= p.K) continue;
+      if (p.splits > 1) {
+        float* dst = p.C + (long long)split * p.split_stride;
+        dst[(long long)m * p.K + k] = acc.v[i][j];
+        if (DUAL) dst[(long long)p.M * p.K + (long long)m * p.K + k] = acc2.v[i][j];
+        continue;
+      }
       float v = acc.v[i][j];
       if (DUAL) v += p.a_scale[k] * acc2.v[i][j];
       if (p.mask && !(p.mask[(long long)m * p.ldc + k] > 0.f)) v = 0.f;

@@ -192,6 +192,29 @@ __global__ void __launch_bounds__(256) finish_tn_kernel(const __grid_constant__ 
   }
 }
 
+struct FinishNT {  // split partials [M][K] (+ dual second half) of up to two NT problems -> summed, masked output
+  const float* partial[2]; const float* a_scale[2]; int nsrc; int splits; long long stride; int M, K; int dual;
+  const float* mask; float* out;
+};
+
+__global__ void __launch_bounds__(256) finish_nt_kernel(FinishNT f) {
+  long long total = (long long)f.M * f.K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int k = (int)(i % f.K);
+    float v = 0.f;
+    for (int q = 0; q < f.nsrc; ++q) {
+      float a = 0.f, b = 0.f;
+      for (int s = 0; s < f.splits; ++s) {
+        a += f.partial[q][s * f.stride + i];
+        if (f.dual) b += f.partial[q][s * f.stride + total + i];
+      }
+      v += f.dual ? a + f.a_scale[q][k] * b : a;
+    }
+    if (f.mask && !(f.mask[i] > 0.f)) v = 0.f;
+    f.out[i] = v;
+  }
+}
+
 // col2im for the conv input gradient: dX[b,y,x,c] = sum over kernel taps of dcol, times ReLU mask.
 __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ dcol, const float* __restrict__ act,
                                                      float* __restrict__ dx, int nimg, int H, int W, int Cin, int KH, int KW,
@@ -627,9 +650,11 @@ __global__ void __launch_bounds__(256) grad_norm_kernel(const float* __restrict_
   __shared__ float s[32];
   __shared__ bool last;
   float acc = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float v = g[i];
-    acc = fmaf(v, v, acc);
+  const long long n4 = n >> 2;   // the blob is padded to a multiple of 4 floats
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = g4[i];
+    acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
@@ -659,6 +684,25 @@ struct OptArgs {
   float* p; const float* g; float* m; float* v; long long n; const float* norm; const int64_t* counters;
 };
 
+__device__ __forceinline__ float opt_one(const OptArgs& o, float p, float g, float& m, float& v, bool clip, float norm,
+                                         float c1, float c2) {
+  if (clip) g = (g / norm) * o.max_norm;
+  float upd;
+  if (o.kind == DZ_ADAM) {  // optax.scale_by_adam: eps outside the sqrt, bias-corrected moments
+    float mu = o.b1 * m + (1.0f - o.b1) * g;
+    float nu = o.b2 * v + (1.0f - o.b2) * g * g;
+    m = mu; v = nu;
+    upd = (mu / c1) / (sqrtf(nu / c2) + o.eps);
+  } else {                  // optax.rmsprop(centered=True): eps inside the sqrt
+    float mu = o.decay * m + (1.0f - o.decay) * g;
+    float nu = o.decay * v + (1.0f - o.decay) * g * g;
+    m = mu; v = nu;
+    upd = g * (1.0f / sqrtf(nu - mu * mu + o.eps));
+  }
+  return p - o.lr * upd;
+}
+
+// 7 floats of traffic per parameter (read p,g,m,v; write p,m,v), 16-byte accesses, grid-stride.
 __global__ void __launch_bounds__(256) optimizer_kernel(OptArgs o) {
   const float norm = o.norm[0];
   const bool clip = o.max_norm > 0.f && !(norm < o.max_norm);  // optax.clip_by_global_norm trigger
@@ -668,22 +712,18 @@ __global__ void __launch_bounds__(256) optimizer_kernel(OptArgs o) {
     c1 = 1.0f - powf(o.b1, t);
     c2 = 1.0f - powf(o.b2, t);
   }
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < o.n; i += (long long)gridDim.x * blockDim.x) {
-    float g = o.g[i];
-    if (clip) g = (g / norm) * o.max_norm;
-    float upd;
-    if (o.kind == DZ_ADAM) {  // optax.scale_by_adam: eps outside the sqrt, bias-corrected moments
-      float mu = o.b1 * o.m[i] + (1.0f - o.b1) * g;
-      float nu = o.b2 * o.v[i] + (1.0f - o.b2) * g * g;
-      o.m[i] = mu; o.v[i] = nu;
-      upd = (mu / c1) / (sqrtf(nu / c2) + o.eps);
-    } else {                  // optax.rmsprop(centered=True): eps inside the sqrt
-      float mu = o.decay * o.m[i] + (1.0f - o.decay) * g;
-      float nu = o.decay * o.v[i] + (1.0f - o.decay) * g * g;
-      o.m[i] = mu; o.v[i] = nu;
-      upd = g * (1.0f / sqrtf(nu - mu * mu + o.eps));
-    }
-    o.p[i] = o.p[i] - o.lr * upd;
+  const long long n4 = o.n >> 2;
+  float4* p4 = reinterpret_cast<float4*>(o.p);
+  const float4* g4 = reinterpret_cast<const float4*>(o.g);
+  float4* m4 = reinterpret_cast<float4*>(o.m);
+  float4* v4 = reinterpret_cast<float4*>(o.v);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 p = p4[i], g = g4[i], m = m4[i], v = v4[i];
+    p.x = opt_one(o, p.x, g.x, m.x, v.x, clip, norm, c1, c2);
+    p.y = opt_one(o, p.y, g.y, m.y, v.y, clip, norm, c1, c2);
+    p.z = opt_one(o, p.z, g.z, m.z, v.z, clip, norm, c1, c2);
+    p.w = opt_one(o, p.w, g.w, m.w, v.w, clip, norm, c1, c2);
+    p4[i] = p; m4[i] = m; v4[i] = v;
   }
 }
 
@@ -709,7 +749,9 @@ struct dz_learner {
   float *act1[3], *act2[3], *act3[3];
   float *h1[3][2], *out[3], *outv[3];      // rainbow: h1[p][0]=adv stream, [1]=val stream; out=adv, outv=val
   float *cosf[3], *hi[3], *E0;             // iqn
-  float* nn_partial;                        // split-K partials for the M=batch FC layers
+  float* nn_partial;                        // split-K partials for the M=batch FC layers and heads
+  float* conv_partial;                      // split-K partials for conv2/conv3 forward
+  float* nt_partial;                        // split partials of the input-gradient (NT) GEMMs
   float *dout, *doutv, *dh1[2], *dact3, *dtmp[2], *dcol, *dact2, *dact1, *dhi;
   float* tn_partial[4];                     // conv1/2/3 wgrad partials, [3] = iqn head/embed partial
   float *loss_terms, *scalars;              // scalars: [0]=norm, [1]=shared-bias scratch.., [8..]=norm partials
@@ -720,7 +762,7 @@ struct dz_learner {
   float *act_noise_zero;                    // zeros (acting without noise is never used; placeholder)
   float* q_scratch;
   int norm_blocks;
-  int fc_splits;
+  int fc_splits, head_splits, conv_splits, nt_splits;
 };
 
 namespace {
@@ -749,8 +791,15 @@ int64_t carve(dz_learner* l, char* base) {
     l->hi[p] = iqn ? w.take<float>(rows * d.feat) : nullptr;
   }
   l->E0 = iqn ? w.take<float>((int64_t)B * nh[0] * d.feat) : nullptr;
-  l->fc_splits = 14;
-  l->nn_partial = w.take<float>((int64_t)kMaxProblems * l->fc_splits * 2 * B * 512);
+  l->fc_splits = 14; l->head_splits = 8; l->conv_splits = 4; l->nt_splits = 8;
+  {
+    int64_t head_n = std::max<int64_t>(d.out, c.num_atoms);
+    int64_t fc = (int64_t)kMaxProblems * l->fc_splits * 2 * B * 512;
+    int64_t hd = (int64_t)kMaxProblems * l->head_splits * 2 * B * head_n;
+    l->nn_partial = w.take<float>(std::max(fc, hd));
+    l->conv_partial = w.take<float>((int64_t)3 * l->conv_splits * B * d.h2 * d.w2 * 64);
+    l->nt_partial = w.take<float>((int64_t)2 * l->nt_splits * 2 * B * std::max<int64_t>(d.feat, 512));
+  }
   int64_t rows0 = (int64_t)B * nh[0];
   l->dout = w.take<float>(rows0 * d.out);
   l->doutv = rb ? w.take<float>((int64_t)B * c.num_atoms) : nullptr;
@@ -836,8 +885,8 @@ int run_nn(const char* tag, GemmBatch& gb, bool dual, void* stream) {
     return launch_batch(tag, gemm_nn_kernel<32, 64, 16, 2, 4, false>, gb, grid, 256, stream);
   }
   if (maxN <= 32 && !dual) {
-    dim3 grid(1, (unsigned)(ceil_div(maxM, 128) * maxS), gb.n);
-    return launch_batch(tag, gemm_nn_kernel<128, 32, 16, 4, 4, false>, gb, grid, 256, stream);
+    dim3 grid(1, (unsigned)(ceil_div(maxM, 64) * maxS), gb.n);
+    return launch_batch(tag, gemm_nn_kernel<64, 32, 16, 4, 4, false>, gb, grid, 128, stream);
   }
   dim3 grid((unsigned)ceil_div(maxN, 64), (unsigned)(ceil_div(maxM, 64) * maxS), gb.n);
   if (dual) return launch_batch(tag, gemm_nn_kernel<64, 64, 16, 4, 4, true>, gb, grid, 256, stream);
@@ -861,17 +910,18 @@ int run_tn(const char* tag, GemmBatch& gb, void* stream) {
 }
 
 int run_nt(const char* tag, GemmBatch& gb, bool dual, void* stream) {
-  int maxM = 0, maxK = 0;
+  int maxM = 0, maxK = 0, maxS = 1;
   for (int i = 0; i < gb.n; ++i) {
     maxM = gb.p[i].M > maxM ? gb.p[i].M : maxM;
     maxK = gb.p[i].K > maxK ? gb.p[i].K : maxK;
+    maxS = gb.p[i].splits > maxS ? gb.p[i].splits : maxS;
   }
   if (maxM <= 32) {
-    dim3 grid((unsigned)ceil_div(maxK, 64), (unsigned)ceil_div(maxM, 32), gb.n);
+    dim3 grid((unsigned)ceil_div(maxK, 64), (unsigned)(ceil_div(maxM, 32) * maxS), gb.n);
     if (dual) return launch_batch(tag, gemm_nt_kernel<32, 64, 16, 2, 4, true>, gb, grid, 256, stream);
     return launch_batch(tag, gemm_nt_kernel<32, 64, 16, 2, 4, false>, gb, grid, 256, stream);
   }
-  dim3 grid((unsigned)ceil_div(maxK, 64), (unsigned)ceil_div(maxM, 64), gb.n);
+  dim3 grid((unsigned)ceil_div(maxK, 64), (unsigned)(ceil_div(maxM, 64) * maxS), gb.n);
   if (dual) return launch_batch(tag, gemm_nt_kernel<64, 64, 16, 4, 4, true>, gb, grid, 256, stream);
   return launch_batch(tag, gemm_nt_kernel<64, 64, 16, 4, 4, false>, gb, grid, 256, stream);
 }
@@ -916,22 +966,29 @@ int forward_torso(dz_learner* l, const TorsoJob* jobs, int njobs, int nimg, void
     gb.p[i] = p;
   }
   DZ_TRY(run_nn("conv1_fwd", gb, false, stream));
-  for (int i = 0; i < njobs; ++i) {   // conv2
-    GemmProblem p = zero_problem();
-    set_conv(p, A_CONV_F32, l->act1[jobs[i].set], nimg, d.h1, d.w1, 32, 4, 4, 2);
-    p.B = jobs[i].params + L.off("conv2/w"); p.bias = jobs[i].params + L.off("conv2/b");
-    p.N = 64; p.ldb = 64; p.ldc = 64; p.relu = 1; p.C = l->act2[jobs[i].set];
-    gb.p[i] = p;
+  // conv2 / conv3: few output tiles (41 / 25 per pass) -> split K four ways so the grid covers the 148 SMs;
+  // finish_nn adds the bias and ReLU.
+  for (int layer = 2; layer <= 3; ++layer) {
+    float* outs[kMaxProblems];
+    for (int i = 0; i < njobs; ++i) {
+      GemmProblem p = zero_problem();
+      if (layer == 2) {
+        set_conv(p, A_CONV_F32, l->act1[jobs[i].set], nimg, d.h1, d.w1, 32, 4, 4, 2);
+        p.B = jobs[i].params + L.off("conv2/w"); p.bias = jobs[i].params + L.off("conv2/b");
+        outs[i] = l->act2[jobs[i].set];
+      } else {
+        set_conv(p, A_CONV_F32, l->act2[jobs[i].set], nimg, d.h2, d.w2, 64, 3, 3, 1);
+        p.B = jobs[i].params + L.off("conv3/w"); p.bias = jobs[i].params + L.off("conv3/b");
+        outs[i] = l->act3[jobs[i].set];
+      }
+      p.N = 64; p.ldb = 64; p.ldc = 64; p.relu = 1;
+      p.splits = l->conv_splits; p.split_stride = (long long)p.M * 64;
+      p.C = l->conv_partial + (long long)i * p.splits * p.split_stride;
+      gb.p[i] = p;
+    }
+    DZ_TRY(run_nn(layer == 2 ? "conv2_fwd" : "conv3_fwd", gb, false, stream));
+    DZ_TRY(finish_nn(gb, outs, false, stream));
   }
-  DZ_TRY(run_nn("conv2_fwd", gb, false, stream));
-  for (int i = 0; i < njobs; ++i) {   // conv3
-    GemmProblem p = zero_problem();
-    set_conv(p, A_CONV_F32, l->act2[jobs[i].set], nimg, d.h2, d.w2, 64, 3, 3, 1);
-    p.B = jobs[i].params + L.off("conv3/w"); p.bias = jobs[i].params + L.off("conv3/b");
-    p.N = 64; p.ldb = 64; p.ldc = 64; p.relu = 1; p.C = l->act3[jobs[i].set];
-    gb.p[i] = p;
-  }
-  DZ_TRY(run_nn("conv3_fwd", gb, false, stream));
   return DZ_OK;
 }
 
@@ -965,10 +1022,17 @@ int forward_heads_plain(dz_learner* l, const Pass* passes, int np, int nimg, voi
     p.a_mode = A_PLAIN; p.A = l->h1[passes[i].head][0]; p.lda = 512; p.M = nimg; p.K = 512;
     p.B = passes[i].params + L.off("head/w"); p.N = d.out; p.ldb = d.out; p.ldc = d.out;
     p.bias = passes[i].params + L.off("head/b"); p.bias_shared = shared ? 1 : 0;
-    p.C = l->out[passes[i].head];
+    outs[i] = l->out[passes[i].head];
+    if (nimg <= 32) {
+      p.splits = l->head_splits; p.split_stride = (long long)nimg * d.out;
+      p.C = l->nn_partial + (long long)i * p.splits * p.split_stride;
+    } else {
+      p.C = outs[i];
+    }
     gb.p[i] = p;
   }
   DZ_TRY(run_nn("head_fwd", gb, false, stream));
+  if (nimg <= 32) DZ_TRY(finish_nn(gb, outs, false, stream));
   return DZ_OK;
 }
 
@@ -1017,11 +1081,20 @@ int forward_heads_rainbow(dz_learner* l, const Pass* passes, int np, int nimg, c
       p.N = n_out; p.ldb = n_out; p.ldc = n_out;
       p.bias = nullptr; p.bias2 = passes[i].params + L.off(pre + "sigma/b");   // with_bias=False: mu has no bias
       p.a_scale = s == 0 ? nz.a2i : nz.v2i; p.c_scale = s == 0 ? nz.a2o : nz.v2o;
-      p.C = s == 0 ? l->out[passes[i].head] : l->outv[passes[i].head];
-      gb.p[2 * i + s] = p;
+      int q = 2 * i + s;
+      outs[q] = s == 0 ? l->out[passes[i].head] : l->outv[passes[i].head];
+      if (nimg <= 32) {
+        int64_t head_n = (int64_t)c.num_actions * c.num_atoms;
+        p.splits = l->head_splits; p.split_stride = (long long)2 * nimg * n_out;
+        p.C = l->nn_partial + (long long)q * l->head_splits * 2 * nimg * head_n;
+      } else {
+        p.C = outs[q];
+      }
+      gb.p[q] = p;
     }
   }
   DZ_TRY(run_nn("noisy2_fwd", gb, true, stream));
+  if (nimg <= 32) DZ_TRY(finish_nn(gb, outs, true, stream));
   return DZ_OK;
 }
 
@@ -1071,6 +1144,17 @@ int forward_heads_iqn(dz_learner* l, const Pass* passes, int np, int nimg, const
 }
 
 // ---- backward ----------------------------------------------------------------------------------
+
+int finish_nt(const GemmProblem* probs, int nsrc, const float* mask, float* out, bool dual, void* stream) {
+  FinishNT f;
+  memset(&f, 0, sizeof(f));
+  f.nsrc = nsrc; f.splits = probs[0].splits; f.stride = probs[0].split_stride; f.M = probs[0].M; f.K = probs[0].K;
+  f.dual = dual ? 1 : 0; f.mask = mask; f.out = out;
+  for (int q = 0; q < nsrc; ++q) { f.partial[q] = probs[q].C; f.a_scale[q] = probs[q].a_scale; }
+  long long total = (long long)f.M * f.K;
+  DZ_LAUNCH(finish_nt_kernel, (unsigned)std::min<long long>(ceil_div(total, 256), 148 * 8), 256, 0, stream, f);
+  return DZ_OK;
+}
 
 // Torso backward from dact3 (already masked by act3 > 0): conv3/conv2/conv1 weight+bias grads.
 int backward_torso(dz_learner* l, const uint8_t* const* rows0, void* stream) {
@@ -1181,9 +1265,12 @@ int backward_plain(dz_learner* l, void* stream) {
   {  // dact3 = dh1 * Wf^T, masked by act3 > 0
     GemmProblem p = zero_problem();
     p.A = l->dh1[0]; p.lda = 512; p.M = B; p.N = 512; p.K = d.feat;
-    p.B = P + L.off("fc1/w"); p.ldb = 512; p.C = l->dact3; p.ldc = d.feat; p.mask = l->act3[0];
+    p.B = P + L.off("fc1/w"); p.ldb = 512; p.ldc = d.feat;
+    // weight-streaming GEMM with a 32-row output: split the reduction so ~400 CTAs keep HBM busy
+    p.splits = l->nt_splits; p.split_stride = (long long)B * d.feat; p.C = l->nt_partial;
     gb.p[0] = p;
     DZ_TRY(run_nt("fc1_dgrad", gb, false, stream));
+    DZ_TRY(finish_nt(gb.p, 1, l->act3[0], l->dact3, false, stream));
   }
   return DZ_OK;
 }
@@ -1217,10 +1304,13 @@ int backward_rainbow(dz_learner* l, const float* noise, void* stream) {
     p.A = s == 0 ? l->dout : l->doutv; p.lda = n_out; p.M = B; p.N = n_out; p.K = 512;
     p.B = P + L.off(pre + "mu/w"); p.B2 = P + L.off(pre + "sigma/w"); p.ldb = n_out;
     p.a_scale = s == 0 ? nz.a2i : nz.v2i; p.c_scale = s == 0 ? nz.a2o : nz.v2o;
-    p.C = l->dh1[s]; p.ldc = 512; p.mask = l->h1[0][s];
+    p.ldc = 512;
+    p.splits = 4; p.split_stride = (long long)2 * B * 512;
+    p.C = l->nt_partial + (long long)s * 4 * p.split_stride;
     gb.p[s] = p;
   }
   DZ_TRY(run_nt("noisy2_dgrad", gb, true, stream));
+  for (int s = 0; s < 2; ++s) DZ_TRY(finish_nt(&gb.p[s], 1, l->h1[0][s], l->dh1[s], true, stream));
   for (int s = 0; s < 2; ++s) {  // first noisy layer weight grads
     std::string pre = std::string(st[s]) + "1/";
     GemmProblem p = zero_problem();
@@ -1237,12 +1327,14 @@ int backward_rainbow(dz_learner* l, const float* noise, void* stream) {
     p.A = l->dh1[s]; p.lda = 512; p.M = B; p.N = 512; p.K = d.feat;
     p.B = P + L.off(pre + "mu/w"); p.B2 = P + L.off(pre + "sigma/w"); p.ldb = 512;
     p.a_scale = s == 0 ? nz.a1i : nz.v1i; p.c_scale = s == 0 ? nz.a1o : nz.v1o;
-    p.C = l->dtmp[s]; p.ldc = d.feat;
+    p.ldc = d.feat;
+    p.splits = l->nt_splits; p.split_stride = (long long)2 * B * d.feat;
+    p.C = l->nt_partial + (long long)s * l->nt_splits * p.split_stride;
     gb.p[s] = p;
   }
   DZ_TRY(run_nt("noisy1_dgrad", gb, true, stream));
-  long long n = (long long)B * d.feat;
-  DZ_LAUNCH(add_mask_kernel, (unsigned)ceil_div(n, 256), 256, 0, stream, l->dtmp[0], l->dtmp[1], l->act3[0], l->dact3, n);
+  // dact3 = (adv-stream + val-stream contributions) * [act3 > 0], summed from the split partials
+  DZ_TRY(finish_nt(gb.p, 2, l->act3[0], l->dact3, true, stream));
   return DZ_OK;
 }
 
@@ -1320,7 +1412,7 @@ int run_optimizer(dz_learner* l, float* user_norm, bool apply, void* stream) {
   if (!apply) return DZ_OK;
   OptArgs o{c.optimizer, c.learning_rate, c.opt_eps, c.rms_decay, c.adam_b1, c.adam_b2, c.max_global_grad_norm,
             l->buf.d_online, l->buf.d_grads, l->buf.d_opt_state, l->buf.d_opt_state + n, n, norm, l->buf.d_counters};
-  DZ_LAUNCH(optimizer_kernel, 592, 256, 0, stream, o);
+  DZ_LAUNCH(optimizer_kernel, 148 * 8, 256, 0, stream, o);
   return DZ_OK;
 }
 

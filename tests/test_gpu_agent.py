@@ -208,4 +208,6 @@ def test_agent_runs_in_run_loop_and_state_round_trips(kind):
   pa, pb = a.learner.get_params(), b.learner.get_params()
   for name in pa:
     np.testing.assert_array_equal(pa[name], pb[name], err_msg=name)
-  assert list(a._replay.ids()) == list(b._replay.ids())
+  ids_a = [i for i, _ in a._replay.get_state()['storage']]
+  ids_b = [i for i, _ in b._replay.get_state()['storage']]
+  assert ids_a == ids_b
