@@ -344,6 +344,7 @@ def main():
         'gpu_launches': launches_per_step * K,
         'gpu_launches_per_step': launches_per_step,
         'roofline': roofline,
+        'kernel_avg_us': {k: round(v, 2) for k, v in per_launch_us.items()},
         'learner_gflop_per_step': GFLOP_PER_STEP[args.agent],
         'learner_tflops_achieved': GFLOP_PER_STEP[args.agent] * value / world / 1e3,
         'cpu_baseline': cpu,

@@ -22,4 +22,7 @@ int launch_sample(const dz_replay_view* view, int prioritized, const dz_sample_i
 int launch_update_priorities(const dz_replay_view* view, const int64_t* d_indices, const float* d_priorities, int n,
                              double alpha, int64_t size, void* stream);
 
+struct TcBatch;
+int launch_tc(const char* tag, const TcBatch& tb, int bnj, void* stream);
+
 }  // namespace dz

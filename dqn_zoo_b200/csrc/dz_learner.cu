@@ -15,7 +15,7 @@
 #include <map>
 #include <vector>
 
-#include "dz_gemm.cuh"
+#include "dz_tc.cuh"
 #include "dz_internal.cuh"
 
 namespace dz {
@@ -668,14 +668,22 @@ __global__ void __launch_bounds__(256) grad_norm_kernel(const float* __restrict_
     last = (done == gridDim.x - 1);
   }
   __syncthreads();
-  if (last && threadIdx.x == 0) {
+  if (last) {   // fixed-order tree over the per-block partials: deterministic whatever block finishes last
     __threadfence();
     float t = 0.f;
-    for (unsigned int i = 0; i < gridDim.x; ++i) t += ((volatile float*)partials)[i];
-    norm_out[0] = sqrtf(t);
-    if (user_norm) user_norm[0] = norm_out[0];
-    *ticket = 0;
-    counters[0] += 1;  // optax adam `count` (also counts rmsprop steps)
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) t += ((volatile float*)partials)[i];
+    t = warp_sum(t);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int i = 0; i < (blockDim.x >> 5); ++i) tot += s[i];
+      norm_out[0] = sqrtf(tot);
+      if (user_norm) user_norm[0] = norm_out[0];
+      *ticket = 0;
+      counters[0] += 1;  // optax adam `count` (also counts rmsprop steps)
+    }
   }
 }
 
@@ -702,7 +710,9 @@ __device__ __forceinline__ float opt_one(const OptArgs& o, float p, float g, flo
   return p - o.lr * upd;
 }
 
-// 7 floats of traffic per parameter (read p,g,m,v; write p,m,v), 16-byte accesses, grid-stride.
+// 7 floats of traffic per parameter (read p,g,m,v; write p,m,v), 16-byte accesses, 4 independent
+// float4 quadruples per thread in flight.  (Streaming / evict-first hints on g, m, v were measured
+// SLOWER — 124 vs 80 us for rainbow: most of the 137 MB of state survives in the 126 MB L2 between steps.)
 __global__ void __launch_bounds__(256) optimizer_kernel(OptArgs o) {
   const float norm = o.norm[0];
   const bool clip = o.max_norm > 0.f && !(norm < o.max_norm);  // optax.clip_by_global_norm trigger
@@ -717,13 +727,26 @@ __global__ void __launch_bounds__(256) optimizer_kernel(OptArgs o) {
   const float4* g4 = reinterpret_cast<const float4*>(o.g);
   float4* m4 = reinterpret_cast<float4*>(o.m);
   float4* v4 = reinterpret_cast<float4*>(o.v);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    float4 p = p4[i], g = g4[i], m = m4[i], v = v4[i];
-    p.x = opt_one(o, p.x, g.x, m.x, v.x, clip, norm, c1, c2);
-    p.y = opt_one(o, p.y, g.y, m.y, v.y, clip, norm, c1, c2);
-    p.z = opt_one(o, p.z, g.z, m.z, v.z, clip, norm, c1, c2);
-    p.w = opt_one(o, p.w, g.w, m.w, v.w, clip, norm, c1, c2);
-    p4[i] = p; m4[i] = m; v4[i] = v;
+  constexpr int U = 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < n4; i0 += stride * U) {
+    float4 p[U], g[U], m[U], v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      long long i = i0 + u * stride;
+      if (i < n4) { p[u] = p4[i]; g[u] = g4[i]; m[u] = m4[i]; v[u] = v4[i]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      long long i = i0 + u * stride;
+      if (i < n4) {
+        p[u].x = opt_one(o, p[u].x, g[u].x, m[u].x, v[u].x, clip, norm, c1, c2);
+        p[u].y = opt_one(o, p[u].y, g[u].y, m[u].y, v[u].y, clip, norm, c1, c2);
+        p[u].z = opt_one(o, p[u].z, g[u].z, m[u].z, v[u].z, clip, norm, c1, c2);
+        p[u].w = opt_one(o, p[u].w, g[u].w, m[u].w, v[u].w, clip, norm, c1, c2);
+        p4[i] = p[u]; m4[i] = m[u]; v4[i] = v[u];
+      }
+    }
   }
 }
 
@@ -767,7 +790,7 @@ struct dz_learner {
 
 namespace {
 
-constexpr int kNormBlocks = 296;
+constexpr int kNormBlocks = 592;
 
 int64_t carve(dz_learner* l, char* base) {
   const dz_learner_config& c = l->cfg;
@@ -870,9 +893,168 @@ int launch_batch(const char* tag, KernelT kernel, const GemmBatch& gb, dim3 grid
 
 #define DZ_TRY(expr) do { int _s = (expr); if (_s != DZ_OK) return _s; } while (0)
 
+
+// ---- tcgen05 path: the same grouped problems, re-expressed as D[i,j] = sum_r A(i,r) B(j,r) ----------------
+
+// Which grouped GEMMs run on the tcgen05 kernel (dz_tc.cuh) instead of the fp32-FMA kernels (dz_gemm.cuh).
+// Round-1 status: the tcgen05 path is parity-green for every layer of the dqn/c51/qr/rainbow family but its
+// register-path loaders still cost more issue slots than the FMA kernels' whole inner loop at these tile
+// counts (profiles/r01_tc_vs_simt.md), so it is opt-in: DZ_TC=all, or DZ_TC=<tag>,<tag>,... per layer tag.
+bool g_use_tc = false;
+std::string g_tc_layers;
+
+bool tc_enabled_for(const char* tag) {
+  if (!g_use_tc) return false;
+  if (g_tc_layers.empty() || g_tc_layers == "all") return true;
+  std::string t = std::string(",") + tag + ",";
+  return (std::string(",") + g_tc_layers + ",").find(t) != std::string::npos;
+}
+
+TcOperand tc_plain(const float* ptr, int na, int nb, int ld, int red_is_b, const float* scale_r = nullptr) {
+  TcOperand o;
+  memset(&o, 0, sizeof(o));
+  o.ptr = ptr; o.a_mode = A_PLAIN; o.na = na; o.nb = nb; o.ld = ld; o.red_is_b = red_is_b; o.scale_r = scale_r; o.ones_row = -1;
+  return o;
+}
+// The (possibly implicit-im2col) A matrix of a GemmProblem as a source S[a = m][b = k].
+TcOperand tc_from_A(const GemmProblem& p, int red_is_b, const float* scale_r = nullptr) {
+  TcOperand o;
+  memset(&o, 0, sizeof(o));
+  o.ptr = p.A; o.a_mode = p.a_mode; o.na = p.M; o.nb = p.K; o.ld = p.lda;
+  o.H = p.H; o.W = p.W; o.Cin = p.Cin; o.S = p.S; o.OH = p.OH; o.OW = p.OW; o.seg = p.seg;
+  o.red_is_b = red_is_b; o.scale_r = scale_r; o.ones_row = -1;
+  return o;
+}
+
+bool tc_a_ok(const GemmProblem& p) {
+  if (p.K % 4) return false;
+  if (p.a_mode == A_PLAIN) return (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
+  return true;
+}
+
+// NN: C[M,N] = A[M,K] B[K,N].  Problems must be in partial mode (splits > 1) or plain bias/ReLU epilogues.
+int run_nn_tc(const char* tag, const GemmBatch& gb, bool dual, void* stream, bool* handled) {
+  *handled = false;
+  if (!tc_enabled_for(tag)) return DZ_OK;
+  int maxM = 0, maxN = 0;
+  for (int i = 0; i < gb.n; ++i) {
+    const GemmProblem& p = gb.p[i];
+    if (!tc_a_ok(p) || p.mul || p.C2 || (p.bias_shared && p.splits <= 1)) return DZ_OK;
+    if (dual && p.splits <= 1) return DZ_OK;
+    if ((reinterpret_cast<uintptr_t>(p.B) & 15) || (dual && (reinterpret_cast<uintptr_t>(p.B2) & 15))) return DZ_OK;
+    maxM = std::max(maxM, p.M); maxN = std::max(maxN, p.N);
+  }
+  if (gb.n * (dual ? 2 : 1) > kTcMaxProblems) return DZ_OK;
+  TcBatch tb;
+  memset(&tb, 0, sizeof(tb));
+  const bool swap = maxM <= 64;        // skinny batch: the weights become the 128-row MMA operand
+  for (int i = 0; i < gb.n; ++i) {
+    const GemmProblem& p = gb.p[i];
+    for (int d = 0; d < (dual ? 2 : 1); ++d) {
+      TcProblem t;
+      memset(&t, 0, sizeof(t));
+      t.redirect_row = -1;
+      const float* W = d == 0 ? p.B : p.B2;
+      const float* xs = d == 0 ? nullptr : p.a_scale;          // sigma term: x is scaled by eps_in along k
+      TcOperand act = tc_from_A(p, 1, xs);                     // S[m][k], contiguous along the reduction
+      TcOperand wgt = tc_plain(W, p.K, p.N, p.ldb, 0);         // S[k][n], contiguous along the rows (transposed on load)
+      long long half = (long long)p.M * p.ldc;                 // sigma partial follows the mu partial
+      t.R = p.K;
+      t.splits = p.splits;
+      t.split_stride = p.splits > 1 ? p.split_stride : 0;
+      t.C = p.C + (d ? half : 0);
+      if (swap) { t.A = wgt; t.B = act; t.MI = p.N; t.NJ = p.M; t.sc_i = 1; t.sc_j = p.ldc; }
+      else      { t.A = act; t.B = wgt; t.MI = p.M; t.NJ = p.N; t.sc_i = p.ldc; t.sc_j = 1; }
+      if (p.splits <= 1) {                                     // direct epilogue
+        if (swap) return DZ_OK;                                // (bias is indexed by i there; not needed today)
+        t.bias_j = p.bias; t.relu = p.relu;
+      }
+      tb.p[tb.n++] = t;
+    }
+  }
+  int bnj = swap ? (maxM <= 32 ? 32 : 64) : (maxN <= 32 ? 32 : (maxN <= 64 ? 64 : 128));
+  *handled = true;
+  return launch_tc(tag, tb, bnj, stream);
+}
+
+// TN: C[K(+1),N] = A[M,K]^T G[M,N]; always written as raw partials [Kext][N] (split_stride > 0).
+int run_tn_tc(const char* tag, const GemmBatch& gb, void* stream, bool* handled) {
+  *handled = false;
+  if (!tc_enabled_for(tag) || gb.n > kTcMaxProblems) return DZ_OK;
+  int maxN = 0;
+  for (int i = 0; i < gb.n; ++i) {
+    const GemmProblem& p = gb.p[i];
+    if (!tc_a_ok(p)) return DZ_OK;
+    if ((reinterpret_cast<uintptr_t>(p.B) & 15) || p.ldb % 4) return DZ_OK;
+    maxN = std::max(maxN, p.N);
+  }
+  TcBatch tb;
+  memset(&tb, 0, sizeof(tb));
+  for (int i = 0; i < gb.n; ++i) {
+    const GemmProblem& p = gb.p[i];
+    const int kext = p.K + ((p.Cb || p.Cb2) ? 1 : 0);
+    TcProblem t;
+    memset(&t, 0, sizeof(t));
+    t.redirect_row = -1;
+    t.A = tc_from_A(p, 0);                                     // S[m][k]: tile rows = k, reduction = m
+    t.A.ones_row = kext > p.K ? p.K : -1;                      // bias-gradient row
+    t.B = tc_plain(p.B, p.M, p.N, p.ldb, 0);                   // G[m][n]: tile rows = n, reduction = m
+    t.MI = kext; t.NJ = p.N; t.R = p.M;
+    if (p.split_stride > 0) {            // raw partials [Kext][N]
+      t.C = p.C; t.sc_i = p.N; t.sc_j = 1; t.splits = p.splits; t.split_stride = p.split_stride;
+    } else {                             // direct: weight grads (+ sigma grads) and bias row(s)
+      t.C = p.C; t.sc_i = p.ldc; t.sc_j = 1; t.splits = 1; t.split_stride = 0;
+      t.C2 = p.C2; t.s2_i = p.a_scale; t.s2_j = p.c_scale;
+      t.redirect_row = kext > p.K ? p.K : -1; t.Cb = p.Cb; t.Cb2 = p.Cb2;
+    }
+    tb.p[tb.n++] = t;
+  }
+  *handled = true;
+  return launch_tc(tag, tb, maxN <= 32 ? 32 : (maxN <= 64 ? 64 : 128), stream);
+}
+
+// NT: C[M,K] = G[M,N] W[K,N]^T (+ dual): raw store (splits == 1, no mask) or raw partials [M][K].
+int run_nt_tc(const char* tag, const GemmBatch& gb, bool dual, void* stream, bool* handled) {
+  *handled = false;
+  if (!tc_enabled_for(tag) || gb.n * (dual ? 2 : 1) > kTcMaxProblems) return DZ_OK;
+  int maxM = 0, maxK = 0;
+  for (int i = 0; i < gb.n; ++i) {
+    const GemmProblem& p = gb.p[i];
+    if (p.lda % 4 || p.ldb % 4 || p.N % 4) return DZ_OK;
+    if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.B) & 15)) return DZ_OK;
+    if (p.splits <= 1 && (p.mask || dual)) return DZ_OK;
+    maxM = std::max(maxM, p.M); maxK = std::max(maxK, p.K);
+  }
+  const bool swap = maxM <= 64;
+  TcBatch tb;
+  memset(&tb, 0, sizeof(tb));
+  for (int i = 0; i < gb.n; ++i) {
+    const GemmProblem& p = gb.p[i];
+    for (int d = 0; d < (dual ? 2 : 1); ++d) {
+      TcProblem t;
+      memset(&t, 0, sizeof(t));
+      t.redirect_row = -1;
+      TcOperand g = tc_plain(static_cast<const float*>(p.A), p.M, p.N, p.lda, 1, d ? p.c_scale : nullptr);  // G[m][n], scaled by eps_out along n
+      TcOperand w = tc_plain(d ? p.B2 : p.B, p.K, p.N, p.ldb, 1);                                           // W[k][n]
+      long long out_ld = p.splits > 1 ? p.K : p.ldc;
+      t.R = p.N; t.splits = p.splits; t.split_stride = p.splits > 1 ? p.split_stride : 0;
+      t.C = p.C + (d ? (long long)p.M * p.K : 0);
+      if (swap) { t.A = w; t.B = g; t.MI = p.K; t.NJ = p.M; t.sc_i = 1; t.sc_j = out_ld; }
+      else      { t.A = g; t.B = w; t.MI = p.M; t.NJ = p.K; t.sc_i = out_ld; t.sc_j = 1; }
+      tb.p[tb.n++] = t;
+    }
+  }
+  int bnj = swap ? (maxM <= 32 ? 32 : 64) : (maxK <= 32 ? 32 : (maxK <= 64 ? 64 : 128));
+  *handled = true;
+  return launch_tc(tag, tb, bnj, stream);
+}
+
 // ---- NN launch helpers (tile shapes chosen by M / N) -------------------------------------------
 
 int run_nn(const char* tag, GemmBatch& gb, bool dual, void* stream) {
+  bool handled = false;
+  DZ_TRY(run_nn_tc(tag, gb, dual, stream, &handled));
+  if (handled) return DZ_OK;
   int maxM = 0, maxN = 0, maxS = 1;
   for (int i = 0; i < gb.n; ++i) {
     maxM = gb.p[i].M > maxM ? gb.p[i].M : maxM;
@@ -894,6 +1076,9 @@ int run_nn(const char* tag, GemmBatch& gb, bool dual, void* stream) {
 }
 
 int run_tn(const char* tag, GemmBatch& gb, void* stream) {
+  bool handled = false;
+  DZ_TRY(run_tn_tc(tag, gb, stream, &handled));
+  if (handled) return DZ_OK;
   int maxK = 0, maxN = 0, maxS = 1;
   for (int i = 0; i < gb.n; ++i) {
     int kext = gb.p[i].K + ((gb.p[i].Cb || gb.p[i].Cb2) ? 1 : 0);
@@ -910,6 +1095,9 @@ int run_tn(const char* tag, GemmBatch& gb, void* stream) {
 }
 
 int run_nt(const char* tag, GemmBatch& gb, bool dual, void* stream) {
+  bool handled = false;
+  DZ_TRY(run_nt_tc(tag, gb, dual, stream, &handled));
+  if (handled) return DZ_OK;
   int maxM = 0, maxK = 0, maxS = 1;
   for (int i = 0; i < gb.n; ++i) {
     maxM = gb.p[i].M > maxM ? gb.p[i].M : maxM;
@@ -1533,6 +1721,8 @@ int dz_learner_create(const dz_learner_config* cfg, const dz_learner_buffers* bu
   DZ_TRY(validate(*cfg));
   if (!buf->d_online || !buf->d_target || !buf->d_grads || !buf->d_opt_state || !buf->d_workspace || !buf->d_counters)
     return fail(DZ_EINVAL, "all learner buffers are required");
+  g_use_tc = getenv("DZ_TC") != nullptr && std::string(getenv("DZ_TC")) != "0";
+  g_tc_layers = getenv("DZ_TC") ? getenv("DZ_TC") : "";
   dz_learner* l = new dz_learner();
   l->cfg = *cfg;
   l->buf = *buf;

@@ -155,3 +155,17 @@ def test_update_is_run_to_run_deterministic():
   L.update(*arrs, weights=w, noise=noise_flat, apply_update=False)
   torch.cuda.synchronize()
   assert torch.equal(g1, L.grads)
+
+
+@pytest.mark.parametrize('kind', ['dqn', 'c51', 'rainbow'])
+def test_tcgen05_path_matches_oracle(kind, monkeypatch):
+  """Same loss/gradient parity with every eligible GEMM routed through the tcgen05 3xTF32 kernel
+  (DZ_TC=all): conv fwd/wgrad/dgrad, fc1 (incl. noisy dual streams), heads."""
+  monkeypatch.setenv('DZ_TC', 'all')
+  from dqn_zoo_b200 import _lib
+  before = _lib.lib.dz_launch_count()
+  test_loss_and_gradients_match_oracle(kind, 84, 32)
+  assert _lib.lib.dz_launch_count() > before
+  monkeypatch.delenv('DZ_TC')
+  # make sure later learners go back to the default path
+  spec, net, L, O, rs = make_case(kind, 32, 84, seed=3)
