@@ -100,6 +100,7 @@ _SIGNATURES = {
     'dz_learner_generate_randomness': (i32, [vp, u64, vp, vp, vp]),
     'dz_learner_q_values': (i32, [vp, vp, vp, vp, vp, vp]),
     'dz_learner_sync_target': (i32, [vp, vp]),
+    'dz_test_u8_to_unit': (i32, [vp, vp]),
     'dz_test_tc_set_variant': (i32, [i32]),
     'dz_test_tc_gemm': (i32, [vp, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp, i32, i32, i32, i64, i64, i32, i64,
                               i32, vp]),

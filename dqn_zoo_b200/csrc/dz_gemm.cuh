@@ -77,6 +77,16 @@ __device__ __forceinline__ ARow a_row_base(const GemmProblem& p, int m) {
   return r;
 }
 
+// x / 255 for an integer 0 <= x <= 255, correctly rounded: identical to __fdiv_rn(x, 255.f) for all 256
+// inputs (checked exhaustively in tests/test_gpu_learner.py), without the IEEE division sequence.
+__device__ __forceinline__ float u8_to_unit(unsigned int x) {
+  const float inv = 0.0039215688593685627f;   // fl32(1/255)
+  float xf = (float)x;
+  float q = xf * inv;
+  float r = fmaf(-q, 255.0f, xf);
+  return fmaf(r, inv, q);
+}
+
 // Four consecutive k (k % 4 == 0) of row r: never straddles a kernel-row segment (seg % 4 == 0).
 __device__ __forceinline__ float4 a_load4(const GemmProblem& p, const ARow& r, int k) {
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -90,10 +100,10 @@ __device__ __forceinline__ float4 a_load4(const GemmProblem& p, const ARow& r, i
       if (r.f) v = *reinterpret_cast<const float4*>(r.f + off);
     } else if (r.u) {
       uchar4 b = *reinterpret_cast<const uchar4*>(r.u + off);
-      v.x = __fdiv_rn((float)b.x, 255.0f);   // x.astype(float32) / 255.0  (networks.py:193)
-      v.y = __fdiv_rn((float)b.y, 255.0f);
-      v.z = __fdiv_rn((float)b.z, 255.0f);
-      v.w = __fdiv_rn((float)b.w, 255.0f);
+      v.x = u8_to_unit(b.x);   // x.astype(float32) / 255.0  (networks.py:193), correctly rounded
+      v.y = u8_to_unit(b.y);
+      v.z = u8_to_unit(b.z);
+      v.w = u8_to_unit(b.w);
     }
   }
   return v;
@@ -172,9 +182,8 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_nn_kernel(const __
   const int per = (kchunks + p.splits - 1) / p.splits;
   const int kc0 = split * per, kc1 = min(kchunks, kc0 + per);
 
-  constexpr int D = DUAL ? 2 : 1;
-  __shared__ __align__(16) float As[2 * D][BK][BM + kPad];   // [buf*D + which]
-  __shared__ __align__(16) float Bs[2 * D][BK][BN + kPad];
+  __shared__ __align__(16) float As[2][BK][BM + kPad];
+  __shared__ __align__(16) float Bs[2][BK][BN + kPad];
 
   const int tid = threadIdx.x, tx = tid % (BN / TN), ty = tid / (BN / TN);
   constexpr int A_VEC = BM * BK / 4, B_VEC = BK * BN / 4;
@@ -187,24 +196,28 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_nn_kernel(const __
   }
   const bool vecB = (p.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0) &&
                     (!DUAL || (reinterpret_cast<uintptr_t>(p.B2) & 15) == 0);
-  Acc<TM, TN> acc, acc2;
+  Acc<TM, TN> acc;
   acc.clear();
-  if (DUAL) acc2.clear();
 
-  float4 ra[A_PER], rs[A_PER], rb[B_PER], rb2[B_PER];
+  // DUAL (noisy layers, networks.py:137-178): y = x Wmu + ((eps_in . x) Wsigma) . eps_out is evaluated as
+  // x (Wmu + Wsigma . (eps_in (x) eps_out)): the effective weight tile is formed while the B tile is staged,
+  // which halves the FMA work and the shared-memory traffic of these layers.
+  float4 ra[A_PER], rb[B_PER];
+  float4 eo[B_PER];                       // eps_out for this thread's 4 columns (fixed over k)
+  if (DUAL) {
+#pragma unroll
+    for (int i = 0; i < B_PER; ++i) {
+      int v = tid + i * NT;
+      int nq = (v % (BN / 4)) * 4;
+      eo[i] = (v < B_VEC) ? ld4_guard(p.c_scale + n0 + nq, n0 + nq, p.N, false) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   auto gload = [&](int kc) {
     const int k0 = kc * BK;
 #pragma unroll
     for (int i = 0; i < A_PER; ++i) {
       int v = tid + i * NT;
-      if (v < A_VEC) {
-        int kq = (v % (BK / 4)) * 4;
-        ra[i] = a_load4(p, rows[i], k0 + kq);
-        if (DUAL) {
-          rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (k0 + kq < p.K) rs[i] = *reinterpret_cast<const float4*>(p.a_scale + k0 + kq);
-        }
-      }
+      if (v < A_VEC) ra[i] = a_load4(p, rows[i], k0 + (v % (BK / 4)) * 4);
     }
 #pragma unroll
     for (int i = 0; i < B_PER; ++i) {
@@ -213,10 +226,16 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_nn_kernel(const __
         int kr = v / (BN / 4), nq = (v % (BN / 4)) * 4;
         int k = k0 + kr, n = n0 + nq;
         rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (DUAL) rb2[i] = rb[i];
         if (k < p.K) {
           rb[i] = ld4_guard(p.B + (long long)k * p.ldb + n, n, p.N, vecB);
-          if (DUAL) rb2[i] = ld4_guard(p.B2 + (long long)k * p.ldb + n, n, p.N, vecB);
+          if (DUAL) {
+            float4 sg = ld4_guard(p.B2 + (long long)k * p.ldb + n, n, p.N, vecB);
+            float ei = p.a_scale[k];
+            rb[i].x = fmaf(sg.x, ei * eo[i].x, rb[i].x);
+            rb[i].y = fmaf(sg.y, ei * eo[i].y, rb[i].y);
+            rb[i].z = fmaf(sg.z, ei * eo[i].z, rb[i].z);
+            rb[i].w = fmaf(sg.w, ei * eo[i].w, rb[i].w);
+          }
         }
       }
     }
@@ -228,23 +247,13 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_nn_kernel(const __
       if (v < A_VEC) {
         int r = v / (BK / 4), kq = (v % (BK / 4)) * 4;
         float4 a = ra[i];
-        float (*A0)[BM + kPad] = As[buf * D];
-        A0[kq + 0][r] = a.x; A0[kq + 1][r] = a.y; A0[kq + 2][r] = a.z; A0[kq + 3][r] = a.w;
-        if (DUAL) {
-          float4 sc = rs[i];
-          float (*A1)[BM + kPad] = As[buf * D + D - 1];
-          A1[kq + 0][r] = a.x * sc.x; A1[kq + 1][r] = a.y * sc.y; A1[kq + 2][r] = a.z * sc.z; A1[kq + 3][r] = a.w * sc.w;
-        }
+        As[buf][kq + 0][r] = a.x; As[buf][kq + 1][r] = a.y; As[buf][kq + 2][r] = a.z; As[buf][kq + 3][r] = a.w;
       }
     }
 #pragma unroll
     for (int i = 0; i < B_PER; ++i) {
       int v = tid + i * NT;
-      if (v < B_VEC) {
-        int kr = v / (BN / 4), nq = (v % (BN / 4)) * 4;
-        *reinterpret_cast<float4*>(&Bs[buf * D][kr][nq]) = rb[i];
-        if (DUAL) *reinterpret_cast<float4*>(&Bs[buf * D + D - 1][kr][nq]) = rb2[i];
-      }
+      if (v < B_VEC) *reinterpret_cast<float4*>(&Bs[buf][v / (BN / 4)][(v % (BN / 4)) * 4]) = rb[i];
     }
   };
 
@@ -254,8 +263,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_nn_kernel(const __
     const int cur = (kc - kc0) & 1;
     const bool more = kc + 1 < kc1;
     if (more) gload(kc + 1);
-    tile_fma<BM, BN, BK, TM, TN, kPad>(As[cur * D], Bs[cur * D], ty, tx, acc);
-    if constexpr (DUAL) tile_fma<BM, BN, BK, TM, TN, kPad>(As[cur * D + 1], Bs[cur * D + 1], ty, tx, acc2);
+    tile_fma<BM, BN, BK, TM, TN, kPad>(As[cur], Bs[cur], ty, tx, acc);
     if (more) sstore(cur ^ 1);
     __syncthreads();
   }
@@ -270,18 +278,12 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_nn_kernel(const __
       int n = n0 + tx * TN + j;
       if (n >= p.N) continue;
       if (p.splits > 1) {
-        float* dst = p.C + (long long)split * p.split_stride;
-        dst[(long long)m * p.ldc + n] = acc.v[i][j];
-        if (DUAL) dst[(long long)p.M * p.ldc + (long long)m * p.ldc + n] = acc2.v[i][j];  // sigma partial right after
+        p.C[(long long)split * p.split_stride + (long long)m * p.ldc + n] = acc.v[i][j];
         continue;
       }
       float v = acc.v[i][j];
       if (p.bias) v += p.bias_shared ? p.bias[0] : p.bias[n];
-      if (DUAL) {
-        float s = acc2.v[i][j];
-        if (p.bias2) s += p.bias2[n];
-        v += s * p.c_scale[n];
-      }
+      if (DUAL && p.bias2) v = fmaf(p.bias2[n], p.c_scale[n], v);
       if (p.relu) v = fmaxf(v, 0.f);
       if (p.mul) {
         if (p.C2) p.C2[(long long)m * p.ldc + n] = v;
@@ -412,20 +414,19 @@ __global__ void __launch_bounds__((BM / TM) * (BNK / TN)) gemm_nt_kernel(const _
   const int nchunks = (p.N + BR - 1) / BR;
   const int per = (nchunks + p.splits - 1) / p.splits;
   const int nc0 = split * per, nc1 = min(nchunks, nc0 + per);
-  constexpr int D = DUAL ? 2 : 1;
-  __shared__ __align__(16) float As[2 * D][BR][BM + kPad];
-  __shared__ __align__(16) float Bs[2 * D][BR][BNK + kPad];
+  __shared__ __align__(16) float As[2][BR][BM + kPad];
+  __shared__ __align__(16) float Bs[2][BR][BNK + kPad];
   const int tid = threadIdx.x, tx = tid % (BNK / TN), ty = tid / (BNK / TN);
   const bool vec = (p.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0) && (p.lda % 4 == 0) &&
                    (!DUAL || (reinterpret_cast<uintptr_t>(p.B2) & 15) == 0);
   const float* G = static_cast<const float*>(p.A);
-  Acc<TM, TN> acc, acc2;
+  Acc<TM, TN> acc;
   acc.clear();
-  if (DUAL) acc2.clear();
   constexpr int A_VEC = BM * BR / 4, B_VEC = BNK * BR / 4;
   constexpr int A_PER = (A_VEC + NT - 1) / NT, B_PER = (B_VEC + NT - 1) / NT;
-  float4 ra[A_PER], rs[A_PER], rb[B_PER], rb2[B_PER];
+  float4 ra[A_PER], rb[B_PER];
+  // DUAL: dx = g (Wmu + Wsigma . (eps_in (x) eps_out))^T — effective weights formed while staging the B tile.
   auto gload = [&](int nc) {
     const int n0 = nc * BR;
 #pragma unroll
@@ -436,7 +437,6 @@ __global__ void __launch_bounds__((BM / TM) * (BNK / TN)) gemm_nt_kernel(const _
         int m = m0 + r, n = n0 + nq;
         ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (m < p.M) ra[i] = ld4_guard(G + (long long)m * p.lda + n, n, p.N, vec);
-        if (DUAL) rs[i] = ld4_guard(p.c_scale + n, n, p.N, false);
       }
     }
 #pragma unroll
@@ -446,10 +446,17 @@ __global__ void __launch_bounds__((BM / TM) * (BNK / TN)) gemm_nt_kernel(const _
         int kr = v / (BR / 4), nq = (v % (BR / 4)) * 4;
         int k = k0 + kr, n = n0 + nq;
         rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (DUAL) rb2[i] = rb[i];
         if (k < p.K) {
           rb[i] = ld4_guard(p.B + (long long)k * p.ldb + n, n, p.N, vec);
-          if (DUAL) rb2[i] = ld4_guard(p.B2 + (long long)k * p.ldb + n, n, p.N, vec);
+          if (DUAL) {
+            float4 sg = ld4_guard(p.B2 + (long long)k * p.ldb + n, n, p.N, vec);
+            float4 eo = ld4_guard(p.c_scale + n, n, p.N, false);
+            float ei = p.a_scale[k];
+            rb[i].x = fmaf(sg.x, ei * eo.x, rb[i].x);
+            rb[i].y = fmaf(sg.y, ei * eo.y, rb[i].y);
+            rb[i].z = fmaf(sg.z, ei * eo.z, rb[i].z);
+            rb[i].w = fmaf(sg.w, ei * eo.w, rb[i].w);
+          }
         }
       }
     }
@@ -461,13 +468,7 @@ __global__ void __launch_bounds__((BM / TM) * (BNK / TN)) gemm_nt_kernel(const _
       if (v < A_VEC) {
         int r = v / (BR / 4), nq = (v % (BR / 4)) * 4;
         float4 g = ra[i];
-        float (*A0)[BM + kPad] = As[buf * D];
-        A0[nq + 0][r] = g.x; A0[nq + 1][r] = g.y; A0[nq + 2][r] = g.z; A0[nq + 3][r] = g.w;
-        if (DUAL) {
-          float4 sc = rs[i];
-          float (*A1)[BM + kPad] = As[buf * D + D - 1];
-          A1[nq + 0][r] = g.x * sc.x; A1[nq + 1][r] = g.y * sc.y; A1[nq + 2][r] = g.z * sc.z; A1[nq + 3][r] = g.w * sc.w;
-        }
+        As[buf][nq + 0][r] = g.x; As[buf][nq + 1][r] = g.y; As[buf][nq + 2][r] = g.z; As[buf][nq + 3][r] = g.w;
       }
     }
 #pragma unroll
@@ -476,13 +477,7 @@ __global__ void __launch_bounds__((BM / TM) * (BNK / TN)) gemm_nt_kernel(const _
       if (v < B_VEC) {
         int kr = v / (BR / 4), nq = (v % (BR / 4)) * 4;
         float4 b = rb[i];
-        float (*B0)[BNK + kPad] = Bs[buf * D];
-        B0[nq + 0][kr] = b.x; B0[nq + 1][kr] = b.y; B0[nq + 2][kr] = b.z; B0[nq + 3][kr] = b.w;
-        if (DUAL) {
-          float4 b2 = rb2[i];
-          float (*B1)[BNK + kPad] = Bs[buf * D + D - 1];
-          B1[nq + 0][kr] = b2.x; B1[nq + 1][kr] = b2.y; B1[nq + 2][kr] = b2.z; B1[nq + 3][kr] = b2.w;
-        }
+        Bs[buf][nq + 0][kr] = b.x; Bs[buf][nq + 1][kr] = b.y; Bs[buf][nq + 2][kr] = b.z; Bs[buf][nq + 3][kr] = b.w;
       }
     }
   };
@@ -492,8 +487,7 @@ __global__ void __launch_bounds__((BM / TM) * (BNK / TN)) gemm_nt_kernel(const _
     const int cur = (nc - nc0) & 1;
     const bool more = nc + 1 < nc1;
     if (more) gload(nc + 1);
-    tile_fma<BM, BNK, BR, TM, TN, kPad>(As[cur * D], Bs[cur * D], ty, tx, acc);
-    if constexpr (DUAL) tile_fma<BM, BNK, BR, TM, TN, kPad>(As[cur * D + 1], Bs[cur * D + 1], ty, tx, acc2);
+    tile_fma<BM, BNK, BR, TM, TN, kPad>(As[cur], Bs[cur], ty, tx, acc);
     if (more) sstore(cur ^ 1);
     __syncthreads();
   }
@@ -507,13 +501,10 @@ __global__ void __launch_bounds__((BM / TM) * (BNK / TN)) gemm_nt_kernel(const _
       int k = k0 + tx * TN + j;
       if (k >= p.K) continue;
       if (p.splits > 1) {
-        float* dst = p.C + (long long)split * p.split_stride;
-        dst[(long long)m * p.K + k] = acc.v[i][j];
-        if (DUAL) dst[(long long)p.M * p.K + (long long)m * p.K + k] = acc2.v[i][j];
+        p.C[(long long)split * p.split_stride + (long long)m * p.K + k] = acc.v[i][j];
         continue;
       }
       float v = acc.v[i][j];
-      if (DUAL) v += p.a_scale[k] * acc2.v[i][j];
       if (p.mask && !(p.mask[(long long)m * p.ldc + k] > 0.f)) v = 0.f;
       p.C[(long long)m * p.ldc + k] = v;
     }

@@ -153,16 +153,10 @@ __global__ void __launch_bounds__(256) finish_nn_kernel(const __grid_constant__ 
   long long total = (long long)f.M * f.N;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int n = (int)(i % f.N);
-    float v = 0.f, s = 0.f;
-    for (int k = 0; k < f.splits; ++k) {
-      v += f.partial[k * f.stride + i];
-      if (f.dual) s += f.partial[k * f.stride + total + i];
-    }
+    float v = 0.f;
+    for (int k = 0; k < f.splits; ++k) v += f.partial[k * f.stride + i];
     if (f.bias) v += f.bias_shared ? f.bias[0] : f.bias[n];
-    if (f.dual) {
-      if (f.bias2) s += f.bias2[n];
-      v += s * f.c_scale[n];
-    }
+    if (f.dual && f.bias2) v = fmaf(f.bias2[n], f.c_scale[n], v);   // sigma bias of the noisy layer
     if (f.relu) v = fmaxf(v, 0.f);
     f.out[i] = v;
   }
@@ -200,15 +194,11 @@ struct FinishNT {  // split partials [M][K] (+ dual second half) of up to two NT
 __global__ void __launch_bounds__(256) finish_nt_kernel(FinishNT f) {
   long long total = (long long)f.M * f.K;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int k = (int)(i % f.K);
     float v = 0.f;
     for (int q = 0; q < f.nsrc; ++q) {
-      float a = 0.f, b = 0.f;
-      for (int s = 0; s < f.splits; ++s) {
-        a += f.partial[q][s * f.stride + i];
-        if (f.dual) b += f.partial[q][s * f.stride + total + i];
-      }
-      v += f.dual ? a + f.a_scale[q][k] * b : a;
+      float a = 0.f;
+      for (int s = 0; s < f.splits; ++s) a += f.partial[q][s * f.stride + i];
+      v += a;
     }
     if (f.mask && !(f.mask[i] > 0.f)) v = 0.f;
     f.out[i] = v;
@@ -399,69 +389,85 @@ __global__ void __launch_bounds__(64) loss_q_kernel(LossArgs L) {
 }
 
 // c51 / rainbow: categorical_[double_]q_learning with categorical_l2_project + cross entropy.
+// One CTA (4 warps) per example.  Softmaxes run one warp per (pass, action) with shuffle reductions, so the
+// whole kernel has five block barriers.
+__device__ __forceinline__ float warp_sum_all(float v) { return warp_sum(v); }
+
 __global__ void __launch_bounds__(128) loss_categorical_kernel(LossArgs L) {
   extern __shared__ float sm[];
-  const int b = blockIdx.x, K = L.atoms, A = L.A, tid = threadIdx.x;
-  float* red = sm;             // [32]
-  float* logit = sm + 32;      // [K] scratch logits
-  float* p_tgt = logit + K;    // [K]
-  float* proj = p_tgt + K;     // [K]
-  float* qsel = proj + K;      // [A]
-  float* colmean = qsel + A;   // [K] rainbow mean over actions of adv
+  const int b = blockIdx.x, K = L.atoms, A = L.A, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* cm_sel = sm;            // [K] mean over actions of the selector-pass advantages (rainbow)
+  float* cm_tgt = cm_sel + K;    // [K] same for the target pass
+  float* cm_tm1 = cm_tgt + K;    // [K] same for the online(s_tm1) pass
+  float* p_tgt = cm_tm1 + K;     // [K]
+  float* proj = p_tgt + K;       // [K]
+  float* p_tm1 = proj + K;       // [K] softmax(logits_tm1[a_tm1])
+  float* qsel = p_tm1 + K;       // [A]
+  float* scal = qsel + A;        // [4]: loss, sum(proj)
   const bool rb = L.kind == DZ_RAINBOW;
-  const float dz_ = 2.0f * L.vmax / (float)(K - 1);
   auto support = [&](int i) { return (float)((double)(-L.vmax) + (double)i * (2.0 * (double)L.vmax / (double)(K - 1))); };
 
-  // logits of (pass, action) into `logit` (rainbow: dueling combine, networks.py:251)
-  auto load_logits = [&](const float* out, const float* adv, const float* val, int a) {
-    if (rb) {
-      for (int k = tid; k < K; k += blockDim.x) {
-        float m = 0.f;
-        for (int aa = 0; aa < A; ++aa) m += adv[((long long)b * A + aa) * K + k];
-        m = m / (float)A;
-        logit[k] = val[(long long)b * K + k] + adv[((long long)b * A + a) * K + k] - m;
+  // 0. dueling column means (networks.py:251: mean over the action axis)
+  if (rb) {
+    for (int k = tid; k < K; k += blockDim.x) {
+      float m1 = 0.f, m2 = 0.f, m0 = 0.f;
+      for (int a = 0; a < A; ++a) {
+        m1 += L.adv1[((long long)b * A + a) * K + k];
+        m2 += L.adv2[((long long)b * A + a) * K + k];
+        m0 += L.adv0[((long long)b * A + a) * K + k];
       }
-    } else {
-      for (int k = tid; k < K; k += blockDim.x) logit[k] = out[((long long)b * A + a) * K + k];
+      cm_sel[k] = m1 / (float)A; cm_tgt[k] = m2 / (float)A; cm_tm1[k] = m0 / (float)A;
     }
-    __syncthreads();
+  }
+  __syncthreads();
+  // logit k of (pass, action): pass 0 = online(s_tm1), 1 = selector, 2 = target
+  auto logit_of = [&](int pass, int a, int k) -> float {
+    if (rb) {
+      const float* adv = pass == 0 ? L.adv0 : (pass == 1 ? L.adv1 : L.adv2);
+      const float* val = pass == 0 ? L.val0 : (pass == 1 ? L.val1 : L.val2);
+      const float* cm = pass == 0 ? cm_tm1 : (pass == 1 ? cm_sel : cm_tgt);
+      return val[(long long)b * K + k] + adv[((long long)b * A + a) * K + k] - cm[k];
+    }
+    const float* out = pass == 0 ? L.out0 : L.out2;   // c51 selects with the target network
+    return out[((long long)b * A + a) * K + k];
   };
-  // softmax statistics of `logit`
-  auto softmax_stats = [&](float& mx, float& denom) {
+  // warp-level softmax of (pass, a): returns this lane's max/denominator; optionally writes probabilities
+  auto warp_softmax = [&](int pass, int a, float* probs, float& mx, float& den) {
     float m = -INFINITY;
-    for (int k = tid; k < K; k += blockDim.x) m = fmaxf(m, logit[k]);
-    mx = block_max(m, red);
+    for (int k = lane; k < K; k += 32) m = fmaxf(m, logit_of(pass, a, k));
+    mx = warp_max(m);
     float s = 0.f;
-    for (int k = tid; k < K; k += blockDim.x) s += expf(logit[k] - mx);
-    denom = block_sum(s, red);
+    for (int k = lane; k < K; k += 32) s += expf(logit_of(pass, a, k) - mx);
+    den = warp_sum(s);
+    if (probs)
+      for (int k = lane; k < K; k += 32) probs[k] = expf(logit_of(pass, a, k) - mx) / den;
   };
 
-  // 1. selector q-values: c51 -> target net on s_t; rainbow -> online net on s_t (pass 1)
-  for (int a = 0; a < A; ++a) {
-    if (rb) load_logits(nullptr, L.adv1, L.val1, a); else load_logits(L.out2, nullptr, nullptr, a);
+  // 1. selector q-values, one warp per action
+  for (int a = warp; a < A; a += 4) {
     float mx, den;
-    softmax_stats(mx, den);
+    warp_softmax(rb ? 1 : 2, a, nullptr, mx, den);
     float s = 0.f;
-    for (int k = tid; k < K; k += blockDim.x) s += (expf(logit[k] - mx) / den) * support(k);
-    s = block_sum(s, red);
-    if (tid == 0) qsel[a] = s;
-    __syncthreads();
+    for (int k = lane; k < K; k += 32) s += (expf(logit_of(rb ? 1 : 2, a, k) - mx) / den) * support(k);
+    s = warp_sum(s);
+    if (lane == 0) qsel[a] = s;
   }
+  __syncthreads();
   int best = 0;
   for (int a = 1; a < A; ++a)
     if (qsel[a] > qsel[best]) best = a;
-  // 2. target distribution p = softmax(target logits[a*])
-  if (rb) load_logits(nullptr, L.adv2, L.val2, best); else load_logits(L.out2, nullptr, nullptr, best);
-  {
-    float mx, den;
-    softmax_stats(mx, den);
-    for (int k = tid; k < K; k += blockDim.x) p_tgt[k] = expf(logit[k] - mx) / den;
-    __syncthreads();
+  const int at = L.a[b];
+  // 2. target distribution (warp 0) and softmax of the taken action's online logits (warp 1)
+  float mx_tm1 = 0.f, den_tm1 = 1.f;
+  if (warp == 0) { float mx, den; warp_softmax(2, best, p_tgt, mx, den); }
+  if (warp == 1) {
+    warp_softmax(0, at, p_tm1, mx_tm1, den_tm1);
+    if (lane == 0) { scal[2] = mx_tm1; scal[3] = den_tm1; }
   }
+  __syncthreads();
   // 3. rlax.categorical_l2_project(r + discount*z, p, z)
   const float r = L.r[b], dsc = L.disc[b];
   const float zmin = support(0), zmax = support(K - 1);
-  (void)dz_;
   for (int i = tid; i < K; i += blockDim.x) {
     float zi = support(i);
     float dpos = (i + 1 < K ? support(i + 1) : support(0)) - zi;      // roll(z,-1) - z
@@ -478,25 +484,25 @@ __global__ void __launch_bounds__(128) loss_categorical_kernel(LossArgs L) {
     proj[i] = acc;
   }
   __syncthreads();
-  // 4. cross entropy with log_softmax(logits_tm1[a_tm1])
-  const int at = L.a[b];
-  if (rb) load_logits(nullptr, L.adv0, L.val0, at); else load_logits(L.out0, nullptr, nullptr, at);
-  float mx, den;
-  softmax_stats(mx, den);
-  const float logden = logf(den);
-  float ls = 0.f, ps = 0.f;
-  for (int k = tid; k < K; k += blockDim.x) {
-    ls += proj[k] * (logit[k] - mx - logden);
-    ps += proj[k];
+  // 4. cross entropy with log_softmax(logits_tm1[a_tm1]) (warp 0)
+  if (warp == 0) {
+    const float mx = scal[2], logden = logf(scal[3]);
+    float ls = 0.f, ps = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      ls += proj[k] * (logit_of(0, at, k) - mx - logden);
+      ps += proj[k];
+    }
+    ls = warp_sum(ls); ps = warp_sum(ps);
+    if (lane == 0) { scal[0] = -ls; scal[1] = ps; }
   }
-  const float loss = -block_sum(ls, red);
-  const float psum = block_sum(ps, red);
+  __syncthreads();
+  const float loss = scal[0], psum = scal[1];
   const float w = L.w ? L.w[b] : 1.0f;
   const float cot = w / (float)L.B;
   // 5. gradient wrt the pass-0 head outputs
   if (rb) {
     for (int k = tid; k < K; k += blockDim.x) {
-      float dl = cot * (expf(logit[k] - mx) / den * psum - proj[k]);
+      float dl = cot * (p_tm1[k] * psum - proj[k]);
       L.dval[(long long)b * K + k] = dl;
       for (int a = 0; a < A; ++a)
         L.dadv[((long long)b * A + a) * K + k] = dl * ((a == at ? 1.0f : 0.0f) - 1.0f / (float)A);
@@ -504,7 +510,7 @@ __global__ void __launch_bounds__(128) loss_categorical_kernel(LossArgs L) {
   } else {
     for (int i = tid; i < A * K; i += blockDim.x) {
       int a = i / K, k = i - a * K;
-      L.dout[(long long)b * A * K + i] = (a == at) ? cot * (expf(logit[k] - mx) / den * psum - proj[k]) : 0.f;
+      L.dout[(long long)b * A * K + i] = (a == at) ? cot * (p_tm1[k] * psum - proj[k]) : 0.f;
     }
   }
   if (tid == 0) {
@@ -512,7 +518,6 @@ __global__ void __launch_bounds__(128) loss_categorical_kernel(LossArgs L) {
     if (L.priorities) L.priorities[b] = fminf(fmaxf(fabsf(loss), 0.f), 100.f);  // rainbow/agent.py:194
     L.loss_terms[b] = w * loss;
   }
-  (void)colmean;
 }
 
 // qrdqn / iqn: rlax.quantile_q_learning with quantile_regression_loss (Huber kappa).
@@ -692,16 +697,20 @@ struct OptArgs {
   float* p; const float* g; float* m; float* v; long long n; const float* norm; const int64_t* counters;
 };
 
+// One parameter.  optax.scale_by_adam divides the moments by (1 - b^t) per element; here the two
+// reciprocals are formed once per thread and multiplied in (<= 1 ulp from the division), leaving one sqrt
+// and one division per parameter instead of four IEEE-division sequences: the kernel was issue-bound.
+template <int KIND>
 __device__ __forceinline__ float opt_one(const OptArgs& o, float p, float g, float& m, float& v, bool clip, float norm,
-                                         float c1, float c2) {
+                                         float inv_c1, float inv_c2) {
   if (clip) g = (g / norm) * o.max_norm;
   float upd;
-  if (o.kind == DZ_ADAM) {  // optax.scale_by_adam: eps outside the sqrt, bias-corrected moments
+  if (KIND == DZ_ADAM) {  // optax.scale_by_adam: eps outside the sqrt, bias-corrected moments
     float mu = o.b1 * m + (1.0f - o.b1) * g;
     float nu = o.b2 * v + (1.0f - o.b2) * g * g;
     m = mu; v = nu;
-    upd = (mu / c1) / (sqrtf(nu / c2) + o.eps);
-  } else {                  // optax.rmsprop(centered=True): eps inside the sqrt
+    upd = (mu * inv_c1) / (sqrtf(nu * inv_c2) + o.eps);
+  } else {                // optax.rmsprop(centered=True): eps inside the sqrt
     float mu = o.decay * m + (1.0f - o.decay) * g;
     float nu = o.decay * v + (1.0f - o.decay) * g * g;
     m = mu; v = nu;
@@ -713,14 +722,15 @@ __device__ __forceinline__ float opt_one(const OptArgs& o, float p, float g, flo
 // 7 floats of traffic per parameter (read p,g,m,v; write p,m,v), 16-byte accesses, 4 independent
 // float4 quadruples per thread in flight.  (Streaming / evict-first hints on g, m, v were measured
 // SLOWER — 124 vs 80 us for rainbow: most of the 137 MB of state survives in the 126 MB L2 between steps.)
+template <int KIND>
 __global__ void __launch_bounds__(256) optimizer_kernel(OptArgs o) {
   const float norm = o.norm[0];
   const bool clip = o.max_norm > 0.f && !(norm < o.max_norm);  // optax.clip_by_global_norm trigger
   float c1 = 1.f, c2 = 1.f;
-  if (o.kind == DZ_ADAM) {
+  if (KIND == DZ_ADAM) {
     float t = (float)o.counters[0];
-    c1 = 1.0f - powf(o.b1, t);
-    c2 = 1.0f - powf(o.b2, t);
+    c1 = 1.0f / (1.0f - powf(o.b1, t));
+    c2 = 1.0f / (1.0f - powf(o.b2, t));
   }
   const long long n4 = o.n >> 2;
   float4* p4 = reinterpret_cast<float4*>(o.p);
@@ -740,10 +750,10 @@ __global__ void __launch_bounds__(256) optimizer_kernel(OptArgs o) {
     for (int u = 0; u < U; ++u) {
       long long i = i0 + u * stride;
       if (i < n4) {
-        p[u].x = opt_one(o, p[u].x, g[u].x, m[u].x, v[u].x, clip, norm, c1, c2);
-        p[u].y = opt_one(o, p[u].y, g[u].y, m[u].y, v[u].y, clip, norm, c1, c2);
-        p[u].z = opt_one(o, p[u].z, g[u].z, m[u].z, v[u].z, clip, norm, c1, c2);
-        p[u].w = opt_one(o, p[u].w, g[u].w, m[u].w, v[u].w, clip, norm, c1, c2);
+        p[u].x = opt_one<KIND>(o, p[u].x, g[u].x, m[u].x, v[u].x, clip, norm, c1, c2);
+        p[u].y = opt_one<KIND>(o, p[u].y, g[u].y, m[u].y, v[u].y, clip, norm, c1, c2);
+        p[u].z = opt_one<KIND>(o, p[u].z, g[u].z, m[u].z, v[u].z, clip, norm, c1, c2);
+        p[u].w = opt_one<KIND>(o, p[u].w, g[u].w, m[u].w, v[u].w, clip, norm, c1, c2);
         p4[i] = p[u]; m4[i] = m[u]; v4[i] = v[u];
       }
     }
@@ -935,7 +945,7 @@ bool tc_a_ok(const GemmProblem& p) {
 // NN: C[M,N] = A[M,K] B[K,N].  Problems must be in partial mode (splits > 1) or plain bias/ReLU epilogues.
 int run_nn_tc(const char* tag, const GemmBatch& gb, bool dual, void* stream, bool* handled) {
   *handled = false;
-  if (!tc_enabled_for(tag)) return DZ_OK;
+  if (!tc_enabled_for(tag) || dual) return DZ_OK;   // noisy (dual) layers: effective-weight FMA kernels
   int maxM = 0, maxN = 0;
   for (int i = 0; i < gb.n; ++i) {
     const GemmProblem& p = gb.p[i];
@@ -1016,7 +1026,7 @@ int run_tn_tc(const char* tag, const GemmBatch& gb, void* stream, bool* handled)
 // NT: C[M,K] = G[M,N] W[K,N]^T (+ dual): raw store (splits == 1, no mask) or raw partials [M][K].
 int run_nt_tc(const char* tag, const GemmBatch& gb, bool dual, void* stream, bool* handled) {
   *handled = false;
-  if (!tc_enabled_for(tag) || gb.n * (dual ? 2 : 1) > kTcMaxProblems) return DZ_OK;
+  if (!tc_enabled_for(tag) || dual || gb.n > kTcMaxProblems) return DZ_OK;
   int maxM = 0, maxK = 0;
   for (int i = 0; i < gb.n; ++i) {
     const GemmProblem& p = gb.p[i];
@@ -1600,7 +1610,8 @@ int run_optimizer(dz_learner* l, float* user_norm, bool apply, void* stream) {
   if (!apply) return DZ_OK;
   OptArgs o{c.optimizer, c.learning_rate, c.opt_eps, c.rms_decay, c.adam_b1, c.adam_b2, c.max_global_grad_norm,
             l->buf.d_online, l->buf.d_grads, l->buf.d_opt_state, l->buf.d_opt_state + n, n, norm, l->buf.d_counters};
-  DZ_LAUNCH(optimizer_kernel, 148 * 8, 256, 0, stream, o);
+  if (c.optimizer == DZ_ADAM) DZ_LAUNCH_NAMED("optimizer_kernel", optimizer_kernel<DZ_ADAM>, 148 * 8, 256, 0, stream, o);
+  else DZ_LAUNCH_NAMED("optimizer_kernel", optimizer_kernel<DZ_RMSPROP_CENTERED>, 148 * 8, 256, 0, stream, o);
   return DZ_OK;
 }
 
@@ -1658,7 +1669,7 @@ int update_impl(dz_learner* l, const dz_batch* batch, const dz_update_outputs* o
   if (c.kind == DZ_DQN || c.kind == DZ_DOUBLE_Q || c.kind == DZ_PRIORITIZED) {
     DZ_LAUNCH(loss_q_kernel, B, 64, 0, stream, L);
   } else if (c.kind == DZ_C51 || c.kind == DZ_RAINBOW) {
-    size_t smem = (32 + 4 * c.num_atoms + c.num_actions) * sizeof(float);
+    size_t smem = (6 * c.num_atoms + c.num_actions + 4) * sizeof(float);
     DZ_LAUNCH(loss_categorical_kernel, B, 128, smem, stream, L);
   } else {
     if (c.kind == DZ_QRDQN) { L.N = c.num_quantiles; L.Ksel = c.num_quantiles; L.Nt = c.num_quantiles; }

@@ -52,6 +52,15 @@ int launch_tc(const char* tag, const TcBatch& tb_in, int bnj, void* stream) {
 
 using namespace dz;
 
+namespace {
+__global__ void u8_to_unit_table_kernel(float* out) { out[threadIdx.x] = u8_to_unit(threadIdx.x); }
+}  // namespace
+
+extern "C" int dz_test_u8_to_unit(float* d_out256, void* stream) {
+  DZ_LAUNCH(u8_to_unit_table_kernel, 1, 256, 0, stream, d_out256);
+  return DZ_OK;
+}
+
 static int g_tc_variant = 0;
 extern "C" int dz_test_tc_set_variant(int32_t v) { g_tc_variant = v; return DZ_OK; }
 

@@ -85,7 +85,8 @@ struct TcBatch {
 namespace tc {
 
 constexpr int kBR = 32;            // reduction elements per k-block (4 MMAs of K = 8)
-constexpr int kLoaderWarps = 8;
+constexpr int kLoaderWarps = 16;    // 4 per SM sub-partition: enough warps in flight to hide the L2 latency of the loads
+constexpr int kEpilogueWarps = 8;   // warps 0..7 drain TMEM (2 per lane quarter)
 constexpr int kLoaders = kLoaderWarps * 32;
 constexpr int kThreads = kLoaders + 32;
 constexpr int kChunkPad = 144;     // 128-byte core matrix + 16 bytes so 8 consecutive chunks hit distinct banks
@@ -158,15 +159,6 @@ struct TileGeo {
   static constexpr int kMNmajSBO = kChunkPad, kMNmajLBO = (ROWS / 4) * kChunkPad;
 };
 
-// x / 255 for an integer 0 <= x <= 255, correctly rounded (== __fdiv_rn(x, 255.f) for all 256 inputs,
-// verified exhaustively): one multiply + one Newton correction instead of the IEEE division sequence.
-__device__ __forceinline__ float u8_to_unit(unsigned int x) {
-  const float inv = 0.0039215688593685627f;   // fl32(1/255)
-  float xf = (float)x;
-  float q = xf * inv;
-  float r = fmaf(-q, 255.0f, xf);
-  return fmaf(r, inv, q);
-}
 __device__ __forceinline__ float4 u8x4_to_unit(uchar4 u) {
   return make_float4(u8_to_unit(u.x), u8_to_unit(u.y), u8_to_unit(u.z), u8_to_unit(u.w));
 }
@@ -240,7 +232,8 @@ __device__ __forceinline__ float4 quad_transpose(float4 v, int lane) {
 // k-block (row decomposition, base pointers, shared-memory offsets) is computed once per CTA.
 template <int ROWS, bool KSRC>
 struct OperandTile {
-  static constexpr int NV = ROWS * kBR / 4 / kLoaders;   // ROWS=128: 4, 64: 2, 32: 1
+  static constexpr int kVec = ROWS * kBR / 4;                         // float4 per tile
+  static constexpr int NV = (kVec + kLoaders - 1) / kLoaders;         // ROWS=128: 2, 64: 1, 32: 1 (half the threads)
   float4 v[2][NV];          // two k-blocks in flight
   const uint8_t* base[NV];  // KSRC: byte address of S[a][0] (conv: of the pixel's patch origin); else of S[0][b] / unused
   int p0[NV], p1[NV];       // KSRC conv: (kh, kr) of the current k-block; !KSRC: (b or conv k-offset, ones-mask)
@@ -250,11 +243,12 @@ struct OperandTile {
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
       const int idx = lt + q * kLoaders;
+      soff[q] = -1; base[q] = nullptr; p0[q] = 0; p1[q] = 0;
+      if (idx >= kVec) continue;
       int row, c;
       if (KSRC) { row = idx >> 3; c = idx & 7; }
       else { int e = idx & 3, t = idx >> 2; row = (t % (ROWS / 4)) * 4 + e; c = t / (ROWS / 4); }
       soff[q] = (row >> 3) * TileGeo<ROWS>::kKmajSBO + c * TileGeo<ROWS>::kKmajLBO + (row & 7) * 16;
-      base[q] = nullptr; p0[q] = 0; p1[q] = 0;
       if (KSRC) {
         const int a = row0 + row;
         if (a < o.na) {
@@ -295,6 +289,7 @@ struct OperandTile {
     for (int q = 0; q < NV; ++q) {
       const int idx = lt + q * kLoaders;
       float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx >= kVec) { v[set][q] = x; continue; }
       if (KSRC) {
         const int c = idx & 7;
         const int b = r0 + c * 4;
@@ -352,6 +347,7 @@ struct OperandTile {
   __device__ __forceinline__ void store(uint8_t* hi, uint8_t* lo, int lt) {
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
+      if (soff[q] < 0) continue;                 // whole warps at a time (kVec is a multiple of 32)
       float4 x = v[set][q];
       if (!KSRC) x = quad_transpose(x, lt);
       split_store(hi, lo, soff[q], x);
@@ -443,6 +439,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
       }
     }
     // ------------------------------------------------------------------ epilogue: TMEM -> global
+    if (warp < kEpilogueWarps) {
     if (nkb > 0) {
       mbar_wait(accum, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -495,8 +492,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         }
       }
     }
+    }
   } else {
-    // ------------------------------------------------------------------ MMA issuer (warp 8)
+    // ------------------------------------------------------------------ MMA issuer (last warp)
     const uint32_t idesc = make_idesc(128, BNJ, 0, 0);          // both operands K-major in shared memory
     const uint32_t a_lbo = TileGeo<128>::kKmajLBO, a_sbo = TileGeo<128>::kKmajSBO;
     const uint32_t b_lbo = TileGeo<BNJ>::kKmajLBO, b_sbo = TileGeo<BNJ>::kKmajSBO;

@@ -285,6 +285,10 @@ int dz_learner_q_values(dz_learner* l, const uint8_t* d_obs, const float* d_taus
 /* target <- online (dqn/agent.py:155-156): device-to-device copy of the blob. */
 int dz_learner_sync_target(dz_learner* l, void* stream);
 
+/* Writes the device's uint8 -> float32/255 conversion of 0..255 (the conv1 operand load, networks.py:193)
+ * into d_out256 so tests can check it is the correctly rounded quotient. */
+int dz_test_u8_to_unit(float* d_out256, void* stream);
+
 /* Debug knob for the self-test below (descriptor variants while bringing the kernel up). */
 int dz_test_tc_set_variant(int32_t v);
 

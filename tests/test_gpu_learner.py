@@ -169,3 +169,13 @@ def test_tcgen05_path_matches_oracle(kind, monkeypatch):
   monkeypatch.delenv('DZ_TC')
   # make sure later learners go back to the default path
   spec, net, L, O, rs = make_case(kind, 32, 84, seed=3)
+
+
+def test_uint8_to_unit_conversion_is_correctly_rounded():
+  """networks.py:193 `x.astype(float32) / 255.0`: the device uses multiply + one Newton step instead of an
+  IEEE division; it must give the correctly rounded quotient for every possible byte."""
+  from dqn_zoo_b200 import _lib
+  out = torch.zeros(256, dtype=torch.float32, device='cuda')
+  _lib.call('dz_test_u8_to_unit', out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+  want = np.arange(256, dtype=np.float32) / np.float32(255.0)
+  np.testing.assert_array_equal(out.cpu().numpy(), want)
