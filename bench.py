@@ -297,17 +297,40 @@ def main():
   }
   name = top[0]
   dur_s = 1e-3 * top[1][1] / top[1][0]
-  if name in alg_bytes:
+  traffic = None
+  try:
+    with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
+      traffic = json.load(f).get(args.agent, {}).get(name)
+  except Exception:
+    traffic = None
+  # dense-contraction kernels: algorithmic FLOPs per launch (2*M*N*K per problem, SURVEY §2.1 shapes)
+  npass = 3 if args.agent in ('rainbow', 'double_q', 'prioritized') else 2
+  nq = 64
+  alg_flops = {
+      'conv1_fwd': npass * B * 400 * 256 * 32 * 2, 'conv2_fwd': npass * B * 81 * 512 * 64 * 2, 'conv3_fwd': npass * B * 49 * 576 * 64 * 2,
+      'conv1_wgrad': B * 400 * 256 * 32 * 2, 'conv2_wgrad': B * 81 * 512 * 64 * 2, 'conv3_wgrad': B * 49 * 576 * 64 * 2,
+      'conv2_dgrad': B * 81 * 512 * 64 * 2, 'conv3_dgrad': B * 49 * 576 * 64 * 2,
+      'iqn_fc1_fwd': 3 * B * nq * 3136 * 512 * 2, 'iqn_fc1_wgrad': B * nq * 3136 * 512 * 2, 'iqn_fc1_dgrad': B * nq * 3136 * 512 * 2,
+      'iqn_embed_fwd': 3 * B * nq * 64 * 3136 * 2, 'iqn_embed_wgrad': B * nq * 64 * 3136 * 2,
+  }
+  if name in alg_bytes and name not in alg_flops:
     achieved = alg_bytes[name] / dur_s / 1e9
     roofline = {'kernel': name, 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-                'frac': achieved / hbm_peak, 'traffic': None, 'alg_bytes_per_launch': alg_bytes[name],
+                'frac': achieved / hbm_peak, 'traffic': traffic, 'alg_bytes_per_launch': alg_bytes[name],
                 'avg_launch_us': 1e6 * dur_s, 'peak_source': peak_src}
+  elif name in alg_flops:
+    achieved = alg_flops[name] / dur_s / 1e12
+    roofline = {'kernel': name, 'bound': 'tensor', 'achieved': achieved, 'peak': tf_peak, 'unit': 'TFLOP/s',
+                'frac': achieved / tf_peak, 'traffic': traffic, 'alg_flops_per_launch': alg_flops[name],
+                'avg_launch_us': 1e6 * dur_s, 'peak_source': peak_src,
+                'note': 'fp32 FMA kernel today (exact-fp32 products for the 1e-5 parity bar); the peak is the measured dense bf16 '
+                        'tensor throughput, i.e. the fraction states how far this contraction is from the tensor-core roofline'}
   else:
     flops = GFLOP_PER_STEP[args.agent] * 1e9
     achieved = flops / (1e-3 * total_ms / prof_steps) / 1e12
     roofline = {'kernel': name, 'bound': 'tensor', 'achieved': achieved, 'peak': tf_peak, 'unit': 'TFLOP/s',
-                'frac': achieved / tf_peak, 'traffic': None, 'avg_launch_us': 1e6 * dur_s, 'peak_source': peak_src,
-                'note': 'whole-step algorithmic FLOPs over summed kernel time (fp32 SIMT path, no tensor cores yet)'}
+                'frac': achieved / tf_peak, 'traffic': traffic, 'avg_launch_us': 1e6 * dur_s, 'peak_source': peak_src,
+                'note': 'whole-step algorithmic FLOPs over summed kernel time'}
   roofline['kernel_time_share'] = share
   roofline['sample_gather'] = {
       'alg_bytes_per_step': 2 * B * 28224 + 12 * B + (20480 if AGENT_SETUP[args.agent][0] else 0),
