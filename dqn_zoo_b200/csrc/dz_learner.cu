@@ -973,6 +973,10 @@ int run_nn_tc(const char* tag, const GemmBatch& gb, bool dual, void* stream, boo
       t.splits = p.splits;
       t.split_stride = p.splits > 1 ? p.split_stride : 0;
       t.C = p.C + (d ? half : 0);
+      if (!swap && p.a_mode == A_CONV_U8) {                    // conv1: raw bytes are exact TF32 numbers; 1/255 rides on the weights
+        act.exact = 1; act.u8_raw = 1;
+        wgt.mul_all = 0.0039215688593685627f;
+      }
       if (swap) { t.A = wgt; t.B = act; t.MI = p.N; t.NJ = p.M; t.sc_i = 1; t.sc_j = p.ldc; }
       else      { t.A = act; t.B = wgt; t.MI = p.M; t.NJ = p.N; t.sc_i = p.ldc; t.sc_j = 1; }
       if (p.splits <= 1) {                                     // direct epilogue
@@ -1008,6 +1012,10 @@ int run_tn_tc(const char* tag, const GemmBatch& gb, void* stream, bool* handled)
     t.redirect_row = -1;
     t.A = tc_from_A(p, 0);                                     // S[m][k]: tile rows = k, reduction = m
     t.A.ones_row = kext > p.K ? p.K : -1;                      // bias-gradient row
+    if (p.a_mode == A_CONV_U8) {                               // conv1 wgrad: exact byte operand, 1/255 applied to the output
+      t.A.exact = 1; t.A.u8_raw = 1; t.A.ones_value = 255.0f;
+      t.out_scale = 0.0039215688593685627f;
+    }
     t.B = tc_plain(p.B, p.M, p.N, p.ldb, 0);                   // G[m][n]: tile rows = n, reduction = m
     t.MI = kext; t.NJ = p.N; t.R = p.M;
     if (p.split_stride > 0) {            // raw partials [Kext][N]

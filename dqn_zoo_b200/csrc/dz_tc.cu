@@ -4,12 +4,12 @@
 
 namespace dz {
 
-template <int BNJ, int STAGES, bool AK, bool BK>
+template <int BNJ, int STAGES, bool AK, bool BK, bool AX>
 static int launch_tc_t(const char* tag, const TcBatch& tb, void* stream) {
   using L = tc::SmemLayout<BNJ, STAGES>;
   static bool configured = false;
   if (!configured) {
-    DZ_CUDA_OK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BNJ, STAGES, AK, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    DZ_CUDA_OK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BNJ, STAGES, AK, BK, AX>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
   int max_i = 0, max_j = 0, max_s = 1;
@@ -19,31 +19,39 @@ static int launch_tc_t(const char* tag, const TcBatch& tb, void* stream) {
     max_s = tb.p[q].splits > max_s ? tb.p[q].splits : max_s;
   }
   dim3 grid((unsigned)ceil_div(max_j, BNJ), (unsigned)(ceil_div(max_i, 128) * max_s), tb.n);
-  DZ_LAUNCH_NAMED(tag, (tc::tc_gemm_kernel<BNJ, STAGES, AK, BK>), grid, tc::kThreads, L::kTotal, stream, tb);
+  DZ_LAUNCH_NAMED(tag, (tc::tc_gemm_kernel<BNJ, STAGES, AK, BK, AX>), grid, tc::kThreads, L::kTotal, stream, tb);
   return DZ_OK;
 }
 
 template <int BNJ, int STAGES>
-static int launch_tc_o(const char* tag, const TcBatch& tb, bool ak, bool bk, void* stream) {
-  if (ak && bk) return launch_tc_t<BNJ, STAGES, true, true>(tag, tb, stream);
-  if (ak && !bk) return launch_tc_t<BNJ, STAGES, true, false>(tag, tb, stream);
-  if (!ak && bk) return launch_tc_t<BNJ, STAGES, false, true>(tag, tb, stream);
-  return launch_tc_t<BNJ, STAGES, false, false>(tag, tb, stream);
+static int launch_tc_o(const char* tag, const TcBatch& tb, bool ak, bool bk, bool ax, void* stream) {
+  if (ax) {   // exact A operand (uint8 observations): only the two shapes conv1 needs
+    if (BNJ == 32 && ak && !bk) return launch_tc_t<32, 4, true, false, true>(tag, tb, stream);    // conv1 forward
+    if (BNJ == 32 && !ak && !bk) return launch_tc_t<32, 4, false, false, true>(tag, tb, stream);  // conv1 weight gradient
+    return fail(DZ_EINVAL, "exact-A tcgen05 path is instantiated for conv1 only");
+  }
+  if (ak && bk) return launch_tc_t<BNJ, STAGES, true, true, false>(tag, tb, stream);
+  if (ak && !bk) return launch_tc_t<BNJ, STAGES, true, false, false>(tag, tb, stream);
+  if (!ak && bk) return launch_tc_t<BNJ, STAGES, false, true, false>(tag, tb, stream);
+  return launch_tc_t<BNJ, STAGES, false, false, false>(tag, tb, stream);
 }
 
 int launch_tc(const char* tag, const TcBatch& tb_in, int bnj, void* stream) {
   if (tb_in.n <= 0 || tb_in.n > kTcMaxProblems) return fail(DZ_EINVAL, "tc batch size");
   TcBatch tb = tb_in;
-  const bool ak = tb.p[0].A.red_is_b != 0, bk = tb.p[0].B.red_is_b != 0;
+  const bool ak = tb.p[0].A.red_is_b != 0, bk = tb.p[0].B.red_is_b != 0, ax = tb.p[0].A.exact != 0;
   for (int q = 0; q < tb.n; ++q) {
-    if ((tb.p[q].A.red_is_b != 0) != ak || (tb.p[q].B.red_is_b != 0) != bk) return fail(DZ_EINVAL, "tc batch mixes operand orientations");
+    if ((tb.p[q].A.red_is_b != 0) != ak || (tb.p[q].B.red_is_b != 0) != bk || (tb.p[q].A.exact != 0) != ax)
+      return fail(DZ_EINVAL, "tc batch mixes operand orientations");
+    if (tb.p[q].A.ones_value == 0.f) tb.p[q].A.ones_value = 1.f;
+    if (tb.p[q].B.ones_value == 0.f) tb.p[q].B.ones_value = 1.f;
     tc_finalize(tb.p[q].A);
     tc_finalize(tb.p[q].B);
   }
   switch (bnj) {
-    case 32: return launch_tc_o<32, 4>(tag, tb, ak, bk, stream);
-    case 64: return launch_tc_o<64, 3>(tag, tb, ak, bk, stream);
-    case 128: return launch_tc_o<128, 3>(tag, tb, ak, bk, stream);   // 2*128 = 256 TMEM columns
+    case 32: return launch_tc_o<32, 4>(tag, tb, ak, bk, ax, stream);
+    case 64: return launch_tc_o<64, 3>(tag, tb, ak, bk, ax, stream);
+    case 128: return launch_tc_o<128, 3>(tag, tb, ak, bk, ax, stream);   // 2*128 = 256 TMEM columns
     default: return fail(DZ_EINVAL, "tc tile N must be 32, 64 or 128");
   }
 }

@@ -53,6 +53,13 @@ struct TcOperand {
   int ones_row;               // tile-row index that reads as 1.0 for every valid r (bias-gradient row), or -1
   FastDiv fd_per, fd_ow, fd_seg;   // conv: OH*OW, OW, seg
   int vec_ok;                 // plain: ld % 4 == 0, nb % 4 == 0 and 16-byte aligned base -> float4 fast path
+  // Exact-operand fast path (conv1): the uint8 observations are exactly representable in TF32, so the
+  // operand is staged as raw integers 0..255 with NO lo part (2 MMAs per k-step instead of 3) and the 1/255 of
+  // networks.py:193 moves onto the other operand (`mul_all`, forward) or the output (`out_scale`, weight grad).
+  int exact;                  // 1: values are exact TF32 numbers, skip the hi/lo split
+  int u8_raw;                 // A_CONV_U8: deliver (float)byte instead of byte/255
+  float mul_all;              // != 0: multiply every element (applied before the split)
+  float ones_value;           // value the ones_row reads as (1, or 255 when the output is scaled by 1/255)
 };
 inline void tc_finalize(TcOperand& o) {
   o.fd_per = make_fastdiv(o.OH * o.OW);
@@ -67,6 +74,7 @@ struct TcProblem {
   float* C;                   // partial s at C + s*split_stride; element (i,j) at i*sc_i + j*sc_j
   long long sc_i, sc_j, split_stride;
   int splits;
+  float out_scale;            // != 0: every output (partial or final) is multiplied by this first
   const float* bias_j;        // optional epilogue (only meaningful with splits == 1): + bias_j[j], then ReLU
   int relu;
   // weight-gradient epilogue (splits == 1): second output C2 = v * s2_i[i] * s2_j[j] (noisy sigma weights) and
@@ -301,7 +309,7 @@ struct OperandTile {
           } else {
             const int off = p0[q] * o.W * o.Cin + p1[q];
             if (o.a_mode == A_CONV_F32) x = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base[q]) + off);
-            else x = u8x4_to_unit(*reinterpret_cast<const uchar4*>(base[q] + off));
+            else { uchar4 u = *reinterpret_cast<const uchar4*>(base[q] + off); x = o.u8_raw ? make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w) : u8x4_to_unit(u); }
           }
           if (o.scale_r) {
             float4 sc = *reinterpret_cast<const float4*>(o.scale_r + b);
@@ -330,27 +338,29 @@ struct OperandTile {
             if (o.a_mode == A_CONV_F32)
               x = *reinterpret_cast<const float4*>(static_cast<const float*>(o.ptr) + (long long)img * o.H * o.W * o.Cin + off);
             else
-              x = u8x4_to_unit(*reinterpret_cast<const uchar4*>(static_cast<const uint8_t* const*>(o.ptr)[img] + off));
+            { uchar4 u = *reinterpret_cast<const uchar4*>(static_cast<const uint8_t* const*>(o.ptr)[img] + off); x = o.u8_raw ? make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w) : u8x4_to_unit(u); }
           }
           if (o.scale_r) { float sc = o.scale_r[a]; x.x *= sc; x.y *= sc; x.z *= sc; x.w *= sc; }
           const int m = p1[q];
-          if (m) { if (m & 1) x.x = 1.f; if (m & 2) x.y = 1.f; if (m & 4) x.z = 1.f; if (m & 8) x.w = 1.f; }
+          if (m) { const float ov = o.ones_value; if (m & 1) x.x = ov; if (m & 2) x.y = ov; if (m & 4) x.z = ov; if (m & 8) x.w = ov; }
         }
       }
+      if (o.mul_all != 0.f) { x.x *= o.mul_all; x.y *= o.mul_all; x.z *= o.mul_all; x.w *= o.mul_all; }
       v[set][q] = x;
     }
   }
 
   // hi/lo split + store of register set `set` (for !KSRC: 4x4 register transpose first; the shuffles
   // sit here, after the loads have landed, so the load instructions stay back to back).
-  template <int set>
+  template <int set, bool EXACT>
   __device__ __forceinline__ void store(uint8_t* hi, uint8_t* lo, int lt) {
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
       if (soff[q] < 0) continue;                 // whole warps at a time (kVec is a multiple of 32)
       float4 x = v[set][q];
       if (!KSRC) x = quad_transpose(x, lt);
-      split_store(hi, lo, soff[q], x);
+      if (EXACT) *reinterpret_cast<float4*>(hi + soff[q]) = x;
+      else split_store(hi, lo, soff[q], x);
     }
   }
 };
@@ -365,7 +375,7 @@ struct SmemLayout {
 
 // grid = (tiles_j, tiles_i * splits, problems); dynamic smem = SmemLayout<BNJ,STAGES>::kTotal.
 // A_KSRC / B_KSRC: the operand's source is contiguous along the reduction index (uniform over the batch).
-template <int BNJ, int STAGES, bool A_KSRC, bool B_KSRC>
+template <int BNJ, int STAGES, bool A_KSRC, bool B_KSRC, bool A_EXACT>
 __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_constant__ TcBatch batch) {
   extern __shared__ __align__(128) uint8_t smem[];
   using L = SmemLayout<BNJ, STAGES>;
@@ -410,12 +420,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
   if (warp < kLoaderWarps) {
     // ------------------------------------------------------------------ loaders
     const int lt = threadIdx.x;
+    // Register copies of the operand descriptors: the mbarrier / fence asm statements below carry "memory"
+    // clobbers, and fields read through `p` (kernel-parameter space, runtime-indexed) would be re-fetched
+    // after every one of them.
+    const TcOperand opA = p.A, opB = p.B;
     OperandTile<128, A_KSRC> ta;
     OperandTile<BNJ, B_KSRC> tb;
-    ta.init(p.A, i0, kb0 * kBR, lt);
-    tb.init(p.B, j0, kb0 * kBR, lt);
-    if (nkb > 0) { ta.template load<0>(p.A, kb0 * kBR, lt); tb.template load<0>(p.B, kb0 * kBR, lt); }
-    if (nkb > 1) { ta.template load<1>(p.A, (kb0 + 1) * kBR, lt); tb.template load<1>(p.B, (kb0 + 1) * kBR, lt); }
+    ta.init(opA, i0, kb0 * kBR, lt);
+    tb.init(opB, j0, kb0 * kBR, lt);
+    if (nkb > 0) { ta.template load<0>(opA, kb0 * kBR, lt); tb.template load<0>(opB, kb0 * kBR, lt); }
+    if (nkb > 1) { ta.template load<1>(opA, (kb0 + 1) * kBR, lt); tb.template load<1>(opB, (kb0 + 1) * kBR, lt); }
     for (int it = 0; it < nkb; ++it) {
       const int s = it % STAGES;
       const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -424,18 +438,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
       const bool more = it + 2 < nkb;
       const int rn = (kb0 + it + 2) * kBR;
       if ((it & 1) == 0) {
-        ta.template store<0>(st, st + L::kA, lt);
-        tb.template store<0>(st + 2 * L::kA, st + 2 * L::kA + L::kB, lt);
+        ta.template store<0, A_EXACT>(st, st + L::kA, lt);
+        tb.template store<0, false>(st + 2 * L::kA, st + 2 * L::kA + L::kB, lt);
       } else {
-        ta.template store<1>(st, st + L::kA, lt);
-        tb.template store<1>(st + 2 * L::kA, st + 2 * L::kA + L::kB, lt);
+        ta.template store<1, A_EXACT>(st, st + L::kA, lt);
+        tb.template store<1, false>(st + 2 * L::kA, st + 2 * L::kA + L::kB, lt);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[s]);
       if (more) {
-        if ((it & 1) == 0) { ta.template load<0>(p.A, rn, lt); tb.template load<0>(p.B, rn, lt); }
-        else               { ta.template load<1>(p.A, rn, lt); tb.template load<1>(p.B, rn, lt); }
+        if ((it & 1) == 0) { ta.template load<0>(opA, rn, lt); tb.template load<0>(opB, rn, lt); }
+        else               { ta.template load<1>(opA, rn, lt); tb.template load<1>(opB, rn, lt); }
       }
     }
     // ------------------------------------------------------------------ epilogue: TMEM -> global
@@ -444,6 +458,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
       mbar_wait(accum, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
+    const int MI = p.MI, NJ = p.NJ, redirect_row = p.redirect_row, relu = p.relu;
+    const long long sc_i = p.sc_i, sc_j = p.sc_j;
+    const float out_scale = p.out_scale;
+    const float* bias_j = p.bias_j; const float* s2_i = p.s2_i; const float* s2_j = p.s2_j;
+    float* C2 = p.C2; float* Cb = p.Cb; float* Cb2 = p.Cb2;
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32)
     const int half = warp >> 2;                   // column halves
     constexpr int kColsPerWarp = BNJ / 2;
@@ -472,21 +491,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
 #pragma unroll
         for (int t = 0; t < 16; ++t) r[t] = 0u;
       }
-      if (i < p.MI) {
+      if (i < MI) {
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
           int j = j0 + col + t;
-          if (j < p.NJ) {
+          if (j < NJ) {
             float v = __uint_as_float(r[t]);
-            if (p.bias_j) v += p.bias_j[j];
-            if (p.relu) v = fmaxf(v, 0.f);
-            if (p.redirect_row >= 0 && i == p.redirect_row) {
-              if (p.Cb) p.Cb[j] = v;
-              if (p.Cb2) p.Cb2[j] = v * p.s2_j[j];
+            if (out_scale != 0.f) v *= out_scale;
+            if (bias_j) v += bias_j[j];
+            if (relu) v = fmaxf(v, 0.f);
+            if (redirect_row >= 0 && i == redirect_row) {
+              if (Cb) Cb[j] = v;
+              if (Cb2) Cb2[j] = v * s2_j[j];
             } else {
-              const long long at = (long long)i * p.sc_i + (long long)j * p.sc_j;
+              const long long at = (long long)i * sc_i + (long long)j * sc_j;
               if (dst) dst[at] = v;
-              if (p.C2) p.C2[at] = v * p.s2_i[i] * p.s2_j[j];
+              if (C2) C2[at] = v * s2_i[i] * s2_j[j];
             }
           }
         }
@@ -515,8 +535,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
           uint64_t dbl = make_desc(b_lo + k * b_step, b_lbo, b_sbo);
           const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
           mma_tf32(tmem_base, dah, dbh, idesc, acc);                 // main accumulator
-          mma_tf32(tmem_base + BNJ, dal, dbh, idesc, acc);           // cross terms
-          mma_tf32(tmem_base + BNJ, dah, dbl, idesc, 1u);
+          if (A_EXACT) {
+            mma_tf32(tmem_base + BNJ, dah, dbl, idesc, acc);         // A has no lo part
+          } else {
+            mma_tf32(tmem_base + BNJ, dal, dbh, idesc, acc);         // cross terms
+            mma_tf32(tmem_base + BNJ, dah, dbl, idesc, 1u);
+          }
         }
         mma_commit(&empty[s]);                    // arrives when the MMAs above have consumed this stage
         if (it == nkb - 1) mma_commit(accum);     // accumulator complete
