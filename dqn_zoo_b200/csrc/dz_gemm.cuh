@@ -19,6 +19,26 @@ namespace dz {
 
 enum : int { A_PLAIN = 0, A_CONV_F32 = 1, A_CONV_U8 = 2 };
 
+// Division by a runtime constant without the integer-divide sequence: q = (umulhi(n, mul) + n) >> shr
+// (round-up method, exact for 0 <= n < 2^31); initialised on the host.
+struct FastDiv {
+  uint32_t mul, shr;
+  int d;
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = d < 1 ? 1 : d;
+  uint32_t s = 0;
+  while ((1u << s) < (uint32_t)f.d) ++s;
+  f.shr = s;
+  f.mul = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << s) - (uint64_t)f.d)) / (uint64_t)f.d + 1);
+  return f;
+}
+__device__ __forceinline__ int fd_div(int n, const FastDiv& f) {
+  return (int)(((uint32_t)__umulhi((uint32_t)n, f.mul) + (uint32_t)n) >> f.shr);
+}
+
+
 struct GemmProblem {
   const void* A;        // A_PLAIN/A_CONV_F32: const float*;  A_CONV_U8: const uint8_t* const* (row table)
   const float* B;       // NN/NT: weights [K,N];  TN: G [M,N]
@@ -29,6 +49,7 @@ struct GemmProblem {
   int lda, ldb, ldc;
   int a_mode;
   int H, W, Cin, KW, S, OH, OW, seg;   // conv geometry: seg = KW*Cin contiguous floats per kernel row
+  FastDiv fd_per, fd_ow, fd_seg;       // OH*OW, OW, seg
   const float* bias;    // NN: [N] (or [1] when bias_shared)
   const float* bias2;   // NN dual: sigma bias [N]
   const float* a_scale; // NN dual: eps_in[K]; NT dual: eps_in[K] (output scale);  TN: eps_in[K]
@@ -65,9 +86,8 @@ __device__ __forceinline__ ARow a_row_base(const GemmProblem& p, int m) {
   if (p.a_mode == A_PLAIN) {
     r.f = static_cast<const float*>(p.A) + (long long)m * p.lda;
   } else {
-    int per = p.OH * p.OW;
-    int img = m / per, rem = m - img * per;
-    int oy = rem / p.OW, ox = rem - oy * p.OW;
+    int img = fd_div(m, p.fd_per), rem = m - img * p.fd_per.d;
+    int oy = fd_div(rem, p.fd_ow), ox = rem - oy * p.fd_ow.d;
     long long off = ((long long)(oy * p.S) * p.W + ox * p.S) * p.Cin;
     if (p.a_mode == A_CONV_F32)
       r.f = static_cast<const float*>(p.A) + (long long)img * p.H * p.W * p.Cin + off;
@@ -94,8 +114,8 @@ __device__ __forceinline__ float4 a_load4(const GemmProblem& p, const ARow& r, i
   if (p.a_mode == A_PLAIN) {
     if (r.f) v = *reinterpret_cast<const float4*>(r.f + k);
   } else {
-    int kh = k / p.seg, rem = k - kh * p.seg;
-    long long off = (long long)kh * p.W * p.Cin + rem;
+    int kh = fd_div(k, p.fd_seg), rem = k - kh * p.fd_seg.d;
+    int off = kh * p.W * p.Cin + rem;
     if (p.a_mode == A_CONV_F32) {
       if (r.f) v = *reinterpret_cast<const float4*>(r.f + off);
     } else if (r.u) {
@@ -122,7 +142,10 @@ struct Acc {
 
 template <int N>
 __device__ __forceinline__ void lds_vec(const float* p, float* out) {
-  if constexpr (N == 4) {
+  if constexpr (N == 8) {
+    float4 t = *reinterpret_cast<const float4*>(p), u = *reinterpret_cast<const float4*>(p + 4);
+    out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w; out[4] = u.x; out[5] = u.y; out[6] = u.z; out[7] = u.w;
+  } else if constexpr (N == 4) {
     float4 t = *reinterpret_cast<const float4*>(p);
     out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
   } else if constexpr (N == 2) {
@@ -378,6 +401,29 @@ __global__ void __launch_bounds__((BMK / TM) * (BN / TN)) gemm_tn_kernel(const _
   for (int i = 0; i < TM; ++i) {
     int k = kk0 + ty * TM + i;
     if (k >= Kext) continue;
+    const int nb = n0 + tx * TN;
+    if (TN == 4 && nb + 3 < p.N && (p.N % 4 == 0) && (p.ldc % 4 == 0 || p.split_stride > 0)) {   // 16-byte stores
+      float4 v4 = make_float4(acc.v[i][0], acc.v[i][1], acc.v[i][2], acc.v[i][3]);
+      if (p.split_stride > 0) {
+        *reinterpret_cast<float4*>(p.C + (long long)split * p.split_stride + (long long)k * p.N + nb) = v4;
+        continue;
+      }
+      if (k < p.K) {
+        if (p.C) *reinterpret_cast<float4*>(p.C + (long long)k * p.ldc + nb) = v4;
+        if (p.C2) {
+          float a = p.a_scale[k];
+          float4 c = *reinterpret_cast<const float4*>(p.c_scale + nb);
+          *reinterpret_cast<float4*>(p.C2 + (long long)k * p.ldc + nb) = make_float4(v4.x * a * c.x, v4.y * a * c.y, v4.z * a * c.z, v4.w * a * c.w);
+        }
+      } else {
+        if (p.Cb) *reinterpret_cast<float4*>(p.Cb + nb) = v4;
+        if (p.Cb2) {
+          float4 c = *reinterpret_cast<const float4*>(p.c_scale + nb);
+          *reinterpret_cast<float4*>(p.Cb2 + nb) = make_float4(v4.x * c.x, v4.y * c.y, v4.z * c.z, v4.w * c.w);
+        }
+      }
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       int n = n0 + tx * TN + j;

@@ -884,6 +884,7 @@ GemmProblem zero_problem() {
   memset(&p, 0, sizeof(p));
   p.splits = 1;
   p.mul_div = 1;
+  p.fd_per = make_fastdiv(1); p.fd_ow = make_fastdiv(1); p.fd_seg = make_fastdiv(1);
   return p;
 }
 
@@ -891,6 +892,7 @@ void set_conv(GemmProblem& p, int mode, const void* A, int nimg, int H, int W, i
   p.a_mode = mode; p.A = A; p.H = H; p.W = W; p.Cin = Cin; p.KW = KW; p.S = S;
   p.OH = conv_out(H, KH, S); p.OW = conv_out(W, KW, S);
   p.seg = KW * Cin;
+  p.fd_per = make_fastdiv(p.OH * p.OW); p.fd_ow = make_fastdiv(p.OW); p.fd_seg = make_fastdiv(p.seg);
   p.M = nimg * p.OH * p.OW;
   p.K = KH * KW * Cin;
 }

@@ -20,25 +20,6 @@
 
 namespace dz {
 
-// Division by a runtime constant without the integer-divide sequence: q = (umulhi(n, mul) + n) >> shr
-// (round-up method, exact for 0 <= n < 2^31); initialised on the host.
-struct FastDiv {
-  uint32_t mul, shr;
-  int d;
-};
-inline FastDiv make_fastdiv(int d) {
-  FastDiv f;
-  f.d = d < 1 ? 1 : d;
-  uint32_t s = 0;
-  while ((1u << s) < (uint32_t)f.d) ++s;
-  f.shr = s;
-  f.mul = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << s) - (uint64_t)f.d)) / (uint64_t)f.d + 1);
-  return f;
-}
-__device__ __forceinline__ int fd_div(int n, const FastDiv& f) {
-  return (int)(((uint32_t)__umulhi((uint32_t)n, f.mul) + (uint32_t)n) >> f.shr);
-}
-
 struct TcOperand {
   // Source matrix S[a][b] with b the contiguous index (same addressing as GemmProblem's A: plain
   // row-major with leading dimension `ld`, or an implicit im2col view of NHWC float / uint8 rows).
