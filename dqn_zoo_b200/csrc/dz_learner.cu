@@ -796,6 +796,11 @@ struct dz_learner {
   float* q_scratch;
   int norm_blocks;
   int fc_splits, head_splits, conv_splits, nt_splits;
+  // second stream for work that is off the critical path of the backward pass (weight gradients, priority
+  // write-back, noise generation); under stream capture it becomes a parallel branch of the CUDA graph
+  cudaStream_t side;
+  cudaEvent_t ev_fork, ev_join;
+  bool side_dirty;
 };
 
 namespace {
@@ -1364,6 +1369,23 @@ int finish_nt(const GemmProblem* probs, int nsrc, const float* mask, float* out,
   return DZ_OK;
 }
 
+// Returns the side stream after making it wait for everything enqueued on `stream` so far (or `stream`
+// itself when there is no side stream).  join_side() makes `stream` wait for the side work again.
+void* fork_side(dz_learner* l, void* stream) {
+  if (!l->side) return stream;
+  if (cudaEventRecord(l->ev_fork, (cudaStream_t)stream) != cudaSuccess) return stream;
+  if (cudaStreamWaitEvent(l->side, l->ev_fork, 0) != cudaSuccess) return stream;
+  l->side_dirty = true;
+  return l->side;
+}
+int join_side(dz_learner* l, void* stream) {
+  if (!l->side || !l->side_dirty) return DZ_OK;
+  DZ_CUDA_OK(cudaEventRecord(l->ev_join, l->side));
+  DZ_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, l->ev_join, 0));
+  l->side_dirty = false;
+  return DZ_OK;
+}
+
 // Torso backward from dact3 (already masked by act3 > 0): conv3/conv2/conv1 weight+bias grads.
 int backward_torso(dz_learner* l, const uint8_t* const* rows0, void* stream) {
   const Dims& d = l->d;
@@ -1383,7 +1405,7 @@ int backward_torso(dz_learner* l, const uint8_t* const* rows0, void* stream) {
     int splits = (int)std::min<int64_t>(32, ceil_div(p.M, 64));
     p.splits = splits; p.split_stride = (long long)(p.K + 1) * 64; p.C = l->tn_partial[2];
     gb.n = 1; gb.p[0] = p;
-    DZ_TRY(run_tn("conv3_wgrad", gb, stream));
+    DZ_TRY(run_tn("conv3_wgrad", gb, fork_side(l, stream)));
     fb.f[fb.n++] = FinishTN{p.C, splits, p.split_stride, p.K, 64, G + L.off("conv3/w"), nullptr, p.Cb, nullptr, nullptr, nullptr};
   }
   // conv3 dgrad: dcol = dpre3 * W3^T ; col2im with ReLU mask of act2
@@ -1406,7 +1428,7 @@ int backward_torso(dz_learner* l, const uint8_t* const* rows0, void* stream) {
     int splits = (int)std::min<int64_t>(32, ceil_div(p.M, 64));
     p.splits = splits; p.split_stride = (long long)(p.K + 1) * 64; p.C = l->tn_partial[1];
     gb.n = 1; gb.p[0] = p;
-    DZ_TRY(run_tn("conv2_wgrad", gb, stream));
+    DZ_TRY(run_tn("conv2_wgrad", gb, fork_side(l, stream)));
     fb.f[fb.n++] = FinishTN{p.C, splits, p.split_stride, p.K, 64, G + L.off("conv2/w"), nullptr, p.Cb, nullptr, nullptr, nullptr};
   }
   // conv2 dgrad
@@ -1429,12 +1451,13 @@ int backward_torso(dz_learner* l, const uint8_t* const* rows0, void* stream) {
     int splits = (int)std::min<int64_t>(64, ceil_div(p.M, 64));
     p.splits = splits; p.split_stride = (long long)(p.K + 1) * 32; p.C = l->tn_partial[0];
     gb.n = 1; gb.p[0] = p;
-    DZ_TRY(run_tn("conv1_wgrad", gb, stream));
+    DZ_TRY(run_tn("conv1_wgrad", gb, fork_side(l, stream)));
     fb.f[fb.n++] = FinishTN{p.C, splits, p.split_stride, p.K, 32, G + L.off("conv1/w"), nullptr, p.Cb, nullptr, nullptr, nullptr};
   }
   dim3 grid((unsigned)ceil_div(577 * 64, 256), fb.n);
-  DZ_LAUNCH(finish_tn_kernel, grid, 256, 0, stream, fb);
-  return DZ_OK;
+  void* ws = l->side && l->side_dirty ? (void*)l->side : stream;   // after conv1_wgrad on the same (side) stream
+  DZ_LAUNCH(finish_tn_kernel, grid, 256, 0, ws, fb);
+  return join_side(l, stream);
 }
 
 int backward_plain(dz_learner* l, void* stream) {
@@ -1452,8 +1475,8 @@ int backward_plain(dz_learner* l, void* stream) {
     p.B = l->dout; p.N = d.out; p.ldb = d.out; p.ldc = d.out;
     p.C = G + L.off("head/w"); p.Cb = shared ? l->scalars + 8 + kNormBlocks : G + L.off("head/b");
     gb.p[0] = p;
-    DZ_TRY(run_tn("head_wgrad", gb, stream));
-    if (shared) DZ_LAUNCH(sum_to_scalar_kernel, 1, 128, 0, stream, l->scalars + 8 + kNormBlocks, d.out, G + L.off("head/b"));
+    DZ_TRY(run_tn("head_wgrad", gb, fork_side(l, stream)));
+    if (shared) DZ_LAUNCH(sum_to_scalar_kernel, 1, 128, 0, (l->side && l->side_dirty ? (void*)l->side : stream), l->scalars + 8 + kNormBlocks, d.out, G + L.off("head/b"));
   }
   {  // dh1 = dout * Wh^T, masked by h1 > 0
     GemmProblem p = zero_problem();
@@ -1468,7 +1491,7 @@ int backward_plain(dz_learner* l, void* stream) {
     p.B = l->dh1[0]; p.N = 512; p.ldb = 512; p.ldc = 512;
     p.C = G + L.off("fc1/w"); p.Cb = G + L.off("fc1/b");
     gb.p[0] = p;
-    DZ_TRY(run_tn("fc1_wgrad", gb, stream));
+    DZ_TRY(run_tn("fc1_wgrad", gb, fork_side(l, stream)));
   }
   {  // dact3 = dh1 * Wf^T, masked by act3 > 0
     GemmProblem p = zero_problem();
@@ -1504,7 +1527,7 @@ int backward_rainbow(dz_learner* l, const float* noise, void* stream) {
     p.a_scale = s == 0 ? nz.a2i : nz.v2i; p.c_scale = s == 0 ? nz.a2o : nz.v2o;
     gb.p[s] = p;
   }
-  DZ_TRY(run_tn("noisy2_wgrad", gb, stream));
+  DZ_TRY(run_tn("noisy2_wgrad", gb, fork_side(l, stream)));
   for (int s = 0; s < 2; ++s) {  // dh1_s
     std::string pre = std::string(st[s]) + "2/";
     int n_out = s == 0 ? c.num_actions * c.num_atoms : c.num_atoms;
@@ -1528,7 +1551,7 @@ int backward_rainbow(dz_learner* l, const float* noise, void* stream) {
     p.a_scale = s == 0 ? nz.a1i : nz.v1i; p.c_scale = s == 0 ? nz.a1o : nz.v1o;
     gb.p[s] = p;
   }
-  DZ_TRY(run_tn("noisy1_wgrad", gb, stream));
+  DZ_TRY(run_tn("noisy1_wgrad", gb, fork_side(l, stream)));
   for (int s = 0; s < 2; ++s) {  // dact3 contributions
     std::string pre = std::string(st[s]) + "1/";
     GemmProblem p = zero_problem();
@@ -1567,7 +1590,7 @@ int backward_iqn(dz_learner* l, void* stream) {
     int splits = (int)std::min<int64_t>(16, ceil_div(M, 64));
     p.splits = splits; p.split_stride = (long long)513 * d.out; p.C = part_head;
     gb.p[0] = p;
-    DZ_TRY(run_tn("iqn_head_wgrad", gb, stream));
+    DZ_TRY(run_tn("iqn_head_wgrad", gb, fork_side(l, stream)));
     fb.f[fb.n++] = FinishTN{p.C, splits, p.split_stride, 512, d.out, G + L.off("head/w"), nullptr, p.Cb, nullptr, nullptr, nullptr};
   }
   {  // dh1
@@ -1583,7 +1606,7 @@ int backward_iqn(dz_learner* l, void* stream) {
     p.B = l->dh1[0]; p.N = 512; p.ldb = 512; p.ldc = 512;
     p.C = G + L.off("fc1/w"); p.Cb = G + L.off("fc1/b");
     gb.p[0] = p;
-    DZ_TRY(run_tn("iqn_fc1_wgrad", gb, stream));
+    DZ_TRY(run_tn("iqn_fc1_wgrad", gb, fork_side(l, stream)));
   }
   {  // dHI = dh1 * Wf^T
     GemmProblem p = zero_problem();
@@ -1602,12 +1625,12 @@ int backward_iqn(dz_learner* l, void* stream) {
     int splits = (int)std::min<int64_t>(16, ceil_div(M, 64));
     p.splits = splits; p.split_stride = (long long)(c.latent_dim + 1) * d.feat; p.C = part_embed;
     gb.p[0] = p;
-    DZ_TRY(run_tn("iqn_embed_wgrad", gb, stream));
+    DZ_TRY(run_tn("iqn_embed_wgrad", gb, fork_side(l, stream)));
     fb.f[fb.n++] = FinishTN{p.C, splits, p.split_stride, c.latent_dim, d.feat, G + L.off("embed/w"), nullptr, p.Cb, nullptr, nullptr, nullptr};
   }
   long long mx = std::max<long long>((long long)513 * d.out, (long long)(c.latent_dim + 1) * d.feat);
   dim3 grid((unsigned)ceil_div(mx, 256), fb.n);
-  DZ_LAUNCH(finish_tn_kernel, grid, 256, 0, stream, fb);
+  DZ_LAUNCH(finish_tn_kernel, grid, 256, 0, (l->side && l->side_dirty ? (void*)l->side : stream), fb);
   return DZ_OK;
 }
 
@@ -1625,8 +1648,10 @@ int run_optimizer(dz_learner* l, float* user_norm, bool apply, void* stream) {
   return DZ_OK;
 }
 
+struct WriteBack { const dz_replay_view* view; const int64_t* indices; const float* priorities; double alpha; };
+
 int update_impl(dz_learner* l, const dz_batch* batch, const dz_update_outputs* out, int apply_update, float* max_seen,
-                void* stream) {
+                const WriteBack* wb, void* stream) {
   const dz_learner_config& c = l->cfg;
   const Dims& d = l->d;
   const int B = l->B;
@@ -1688,6 +1713,9 @@ int update_impl(dz_learner* l, const dz_batch* batch, const dz_update_outputs* o
     DZ_LAUNCH(loss_quantile_kernel, B, 256, smem, stream, L);
   }
   DZ_LAUNCH(loss_mean_kernel, 1, 32, 0, stream, l->loss_terms, B, out->d_loss, max_seen, L.priorities);
+  if (wb) {   // replay.update_priorities(ids, priorities) (rainbow/agent.py:198): independent of the backward pass
+    DZ_TRY(launch_update_priorities(wb->view, wb->indices, wb->priorities, B, wb->alpha, wb->view->capacity, fork_side(l, stream)));
+  }
 
   // ---- backward through online(s_tm1)
   if (c.kind == DZ_RAINBOW) DZ_TRY(backward_rainbow(l, batch->d_noise, stream));
@@ -1696,6 +1724,7 @@ int update_impl(dz_learner* l, const dz_batch* batch, const dz_update_outputs* o
   DZ_TRY(backward_torso(l, batch->d_s_tm1_rows, stream));
 
   // ---- clip_by_global_norm + adam / rmsprop + apply_updates
+  DZ_TRY(join_side(l, stream));
   DZ_TRY(run_optimizer(l, out->d_grad_norm, apply_update != 0, stream));
   return DZ_OK;
 }
@@ -1751,16 +1780,31 @@ int dz_learner_create(const dz_learner_config* cfg, const dz_learner_buffers* bu
   l->d = make_dims(*cfg);
   l->B = cfg->batch;
   carve(l, static_cast<char*>(buf->d_workspace));
+  l->side = nullptr; l->ev_fork = nullptr; l->ev_join = nullptr; l->side_dirty = false;
+  if (getenv("DZ_NO_SIDE_STREAM") == nullptr) {
+    if (cudaStreamCreateWithFlags(&l->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&l->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&l->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      l->side = nullptr;
+      cudaGetLastError();
+    }
+  }
   cudaError_t e = cudaMemset(l->ticket, 0, 16);
   if (e != cudaSuccess) { delete l; return fail(DZ_ECUDA, "cudaMemset: %s", cudaGetErrorString(e)); }
   *out = l;
   return DZ_OK;
 }
 
-void dz_learner_destroy(dz_learner* l) { delete l; }
+void dz_learner_destroy(dz_learner* l) {
+  if (!l) return;
+  if (l->side) { cudaStreamSynchronize(l->side); cudaStreamDestroy(l->side); }
+  if (l->ev_fork) cudaEventDestroy(l->ev_fork);
+  if (l->ev_join) cudaEventDestroy(l->ev_join);
+  delete l;
+}
 
 int dz_learner_update(dz_learner* l, const dz_batch* batch, const dz_update_outputs* out, int32_t apply_update, void* stream) {
-  return update_impl(l, batch, out, apply_update, nullptr, stream);
+  return update_impl(l, batch, out, apply_update, nullptr, nullptr, stream);
 }
 
 int dz_learner_learn(dz_learner* l, const dz_replay_view* replay, int32_t prioritized, const dz_learn_io* io, void* stream) {
@@ -1774,13 +1818,9 @@ int dz_learner_learn(dz_learner* l, const dz_replay_view* replay, int32_t priori
   batch.d_a_tm1 = l->s_a; batch.d_r_t = l->s_r; batch.d_discount_t = l->s_d;
   batch.d_weights = prioritized ? l->s_w : nullptr;
   batch.d_taus = io->d_taus; batch.d_noise = io->d_noise;
-  DZ_TRY(update_impl(l, &batch, &io->update_out, 1, io->d_max_seen_priority, stream));
-  if (prioritized) {
-    if (!io->update_out.d_priorities) return fail(DZ_EINVAL, "prioritized learn needs update_out.d_priorities");
-    // replay.update_priorities(ids, priorities)  (rainbow/agent.py:198)
-    DZ_TRY(launch_update_priorities(replay, io->sample_out.d_indices, io->update_out.d_priorities, B, io->priority_exponent,
-                                    replay->capacity, stream));
-  }
+  WriteBack wb{replay, io->sample_out.d_indices, io->update_out.d_priorities, io->priority_exponent};
+  if (prioritized && !io->update_out.d_priorities) return fail(DZ_EINVAL, "prioritized learn needs update_out.d_priorities");
+  DZ_TRY(update_impl(l, &batch, &io->update_out, 1, io->d_max_seen_priority, prioritized ? &wb : nullptr, stream));
   return DZ_OK;
 }
 
