@@ -796,6 +796,12 @@ struct dz_learner {
   float* q_scratch;
   int norm_blocks;
   int fc_splits, head_splits, conv_splits, nt_splits;
+  // packed-operand tcgen05 path of the IQN 3136->512 layer (dz_tcp.cuh): hi/lo tile images + split partials
+  bool pk_on;
+  struct PkImg { float* hi; float* lo; int rows_pad, red_pad; };
+  PkImg pk_act[3], pk_wT[2], pk_w, pk_actT, pk_dh1T, pk_dh1, pk_cos[3], pk_weT[2];
+  float *pk_fwd_partial, *pk_wgrad_partial;
+  int pk_fwd_splits, pk_wgrad_splits;
   // second stream for work that is off the critical path of the backward pass (weight gradients, priority
   // write-back, noise generation); under stream capture it becomes a parallel branch of the CUDA graph
   cudaStream_t side;
@@ -806,6 +812,22 @@ struct dz_learner {
 namespace {
 
 constexpr int kNormBlocks = 592;
+
+// The packed-operand tcgen05 kernels carry IQN's 3136->512 layer whenever every network apply has >= 1024 rows
+// (DZ_PK_IQN=0 falls back to the fp32-FMA kernels, for A/B timing).
+bool g_pk_iqn = true;
+void read_env();
+
+// Split count for a one-CTA-per-SM kernel: minimise (waves of 148 CTAs) x (k-blocks per split).
+int pick_splits(int64_t tiles, int nkb, int max_splits) {
+  int best = 1;
+  int64_t best_cost = -1;
+  for (int s = 1; s <= max_splits; ++s) {
+    int64_t cost = ceil_div(tiles * s, 148) * (ceil_div(nkb, s) + 6);   // +6: pipeline fill/drain per CTA
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+  }
+  return best;
+}
 
 int64_t carve(dz_learner* l, char* base) {
   const dz_learner_config& c = l->cfg;
@@ -855,6 +877,33 @@ int64_t carve(dz_learner* l, char* base) {
   l->tn_partial[1] = w.take<float>((int64_t)32 * 513 * 64);
   l->tn_partial[2] = w.take<float>((int64_t)32 * 577 * 64);
   l->tn_partial[3] = iqn ? w.take<float>((int64_t)16 * (c.latent_dim + 1) * d.feat + 16 * 513 * 64) : nullptr;
+  l->pk_on = false;
+  if (iqn && g_pk_iqn && rows0 >= 1024 && (int64_t)B * nh[1] >= 1024 && (int64_t)B * nh[2] >= 1024 && d.feat % 16 == 0 &&
+      c.latent_dim <= 128 && rows0 % 4 == 0 && ((int64_t)B * nh[1]) % 4 == 0 && ((int64_t)B * nh[2]) % 4 == 0) {
+    l->pk_on = true;
+    auto img = [&](dz_learner::PkImg& im, int64_t rows, int64_t red, int row_tile) {
+      im.rows_pad = (int)(ceil_div(rows, row_tile) * row_tile);
+      im.red_pad = (int)(ceil_div(red, kPkKB) * kPkKB);
+      im.hi = w.take<float>(pk_image_floats(im.rows_pad, im.red_pad));
+      im.lo = w.take<float>(pk_image_floats(im.rows_pad, im.red_pad));
+    };
+    int64_t tiles = 0;
+    for (int p = 0; p < 3; ++p) { img(l->pk_act[p], (int64_t)B * nh[p], d.feat, 128); tiles += l->pk_act[p].rows_pad / 128 * 2; }
+    img(l->pk_wT[0], 512, d.feat, 256);
+    img(l->pk_wT[1], 512, d.feat, 256);
+    img(l->pk_w, d.feat, 512, 256);
+    img(l->pk_actT, d.feat + 1, rows0, 128);
+    img(l->pk_dh1T, 512, rows0, 256);
+    img(l->pk_dh1, rows0, 512, 128);
+    for (int p = 0; p < 3; ++p) img(l->pk_cos[p], (int64_t)B * nh[p], c.latent_dim, 128);
+    img(l->pk_weT[0], d.feat, c.latent_dim, 256);
+    img(l->pk_weT[1], d.feat, c.latent_dim, 256);
+    l->pk_fwd_splits = pick_splits(tiles, l->pk_act[0].red_pad / kPkKB, 6);
+    l->pk_wgrad_splits = pick_splits((int64_t)l->pk_actT.rows_pad / 128 * 2, l->pk_actT.red_pad / kPkKB, 8);
+    int64_t fwd_rows = (int64_t)B * (nh[0] + nh[1] + nh[2]);
+    l->pk_fwd_partial = w.take<float>((int64_t)l->pk_fwd_splits * fwd_rows * 512);
+    l->pk_wgrad_partial = w.take<float>((int64_t)l->pk_wgrad_splits * (d.feat + 1) * 512);
+  }
   l->loss_terms = w.take<float>(B);
   l->scalars = w.take<float>(8 + kNormBlocks + d.out + 64);
   l->ticket = w.take<unsigned int>(4);
@@ -919,6 +968,12 @@ int launch_batch(const char* tag, KernelT kernel, const GemmBatch& gb, dim3 grid
 // counts (profiles/r01_tc_vs_simt.md), so it is opt-in: DZ_TC=all, or DZ_TC=<tag>,<tag>,... per layer tag.
 bool g_use_tc = false;
 std::string g_tc_layers;
+
+void read_env() {
+  g_use_tc = getenv("DZ_TC") != nullptr && std::string(getenv("DZ_TC")) != "0";
+  g_tc_layers = getenv("DZ_TC") ? getenv("DZ_TC") : "";
+  g_pk_iqn = !(getenv("DZ_PK_IQN") != nullptr && std::string(getenv("DZ_PK_IQN")) == "0");
+}
 
 bool tc_enabled_for(const char* tag) {
   if (!g_use_tc) return false;
@@ -1311,6 +1366,83 @@ int forward_heads_rainbow(dz_learner* l, const Pass* passes, int np, int nimg, c
   return DZ_OK;
 }
 
+// IQN embedding (latent -> 3136, ReLU, * state embedding) and 3136 -> 512 layer of the three network applies of
+// one update on the packed-operand tcgen05 kernels: one pack launch (cosine features + every weight operand of
+// this step), the embedding GEMM whose epilogue writes the hi/lo tile images of the next GEMMs directly (the fp32
+// `hi` tensors are never materialised), the split fc1 GEMM, one finish (bias + ReLU).
+int iqn_embed_fc1_forward_packed(dz_learner* l, const Pass* passes, const GemmBatch& fc1, bool keep_E0, void* stream) {
+  const Dims& d = l->d;
+  const Layout& L = l->lay;
+  const dz_learner_config& c = l->cfg;
+  PackBatch pb;
+  memset(&pb, 0, sizeof(pb));
+  const float* blob[2] = {nullptr, nullptr};   // distinct parameter blobs (online first)
+  int widx[3];
+  for (int i = 0; i < 3; ++i) {
+    int k = 0;
+    while (k < 2 && blob[k] && blob[k] != passes[i].params) ++k;
+    if (k == 2) return fail(DZ_EINVAL, "iqn packed path expects at most two parameter blobs");
+    blob[k] = passes[i].params; widx[i] = k;
+    int hp = passes[i].head;
+    const dz_learner::PkImg& im = l->pk_cos[hp];
+    DZ_TRY(pk_add_job(pb, l->cosf[hp], c.latent_dim, 1, fc1.p[i].M, c.latent_dim, im.rows_pad, im.red_pad, -1, im.hi, im.lo));
+  }
+  for (int k = 0; k < 2; ++k) {
+    if (!blob[k]) continue;
+    DZ_TRY(pk_add_job(pb, blob[k] + L.off("embed/w"), d.feat, 0, d.feat, c.latent_dim, l->pk_weT[k].rows_pad, l->pk_weT[k].red_pad,
+                      -1, l->pk_weT[k].hi, l->pk_weT[k].lo));
+    DZ_TRY(pk_add_job(pb, blob[k] + L.off("fc1/w"), 512, 0, 512, d.feat, l->pk_wT[k].rows_pad, l->pk_wT[k].red_pad, -1,
+                      l->pk_wT[k].hi, l->pk_wT[k].lo));
+  }
+  // backward-time operand that only depends on forward-time tensors: W (rows k, reduction n) for the input gradient
+  DZ_TRY(pk_add_job(pb, l->buf.d_online + L.off("fc1/w"), 512, 1, d.feat, 512, l->pk_w.rows_pad, l->pk_w.red_pad, -1, l->pk_w.hi, l->pk_w.lo));
+  DZ_TRY(launch_pack("iqn_pack_fwd", pb, stream));
+
+  PkBatch eb;
+  memset(&eb, 0, sizeof(eb));
+  eb.n = 3;
+  for (int i = 0; i < 3; ++i) {
+    int hp = passes[i].head;
+    PkProblem& p = eb.p[i];
+    p.A = PkOperand{l->pk_cos[hp].hi, l->pk_cos[hp].lo, l->pk_cos[hp].rows_pad / 8};
+    p.B = PkOperand{l->pk_weT[widx[i]].hi, l->pk_weT[widx[i]].lo, l->pk_weT[widx[i]].rows_pad / 8};
+    p.MI = fc1.p[i].M; p.NJ = d.feat; p.nkb = l->pk_cos[hp].red_pad / kPkKB; p.splits = 1;
+    p.bias_j = passes[i].params + L.off("embed/b");
+    p.mul = l->act3[passes[i].set]; p.mul_div = l->n_head[hp]; p.mul_ld = d.feat;
+    p.e0 = (keep_E0 && hp == 0) ? l->E0 : nullptr; p.e0_ld = d.feat;
+    p.img_hi = l->pk_act[hp].hi; p.img_lo = l->pk_act[hp].lo; p.img_rg = l->pk_act[hp].rows_pad / 8;
+    if (keep_E0 && hp == 0) { p.imgT_hi = l->pk_actT.hi; p.imgT_lo = l->pk_actT.lo; p.imgT_rg = l->pk_actT.rows_pad / 8; }
+  }
+  DZ_TRY(launch_pgemm("iqn_embed_fwd", eb, stream, 1));
+
+  PkBatch kb;
+  memset(&kb, 0, sizeof(kb));
+  kb.n = 3;
+  kb.run_kb = 2;     // forward: feeds the ReLU mask and the quantile targets -> fp32-FMA-chain accuracy
+  GemmBatch fin = fc1;
+  float* outs[kMaxProblems] = {nullptr};
+  long long off = 0;
+  for (int i = 0; i < 3; ++i) {
+    int hp = passes[i].head;
+    const dz_learner::PkImg& im = l->pk_act[hp];
+    PkProblem& p = kb.p[i];
+    p.A = PkOperand{im.hi, im.lo, im.rows_pad / 8};
+    p.B = PkOperand{l->pk_wT[widx[i]].hi, l->pk_wT[widx[i]].lo, l->pk_wT[widx[i]].rows_pad / 8};
+    p.MI = fc1.p[i].M; p.NJ = 512; p.nkb = im.red_pad / kPkKB;
+    p.sc_i = 512; p.sc_j = 1; p.splits = l->pk_fwd_splits;
+    p.split_stride = (long long)p.MI * 512;
+    p.C = l->pk_fwd_partial + off;
+    off += (long long)p.splits * p.split_stride;
+    p.bias_j = fc1.p[i].bias; p.relu = 1;
+    if (p.splits == 1) p.C = fc1.p[i].C;
+    fin.p[i].C = p.C; fin.p[i].splits = p.splits; fin.p[i].split_stride = p.split_stride;
+    outs[i] = fc1.p[i].C;
+  }
+  DZ_TRY(launch_pgemm("iqn_fc1_fwd", kb, stream));
+  if (l->pk_fwd_splits > 1) DZ_TRY(finish_nn(fin, outs, false, stream));
+  return DZ_OK;
+}
+
 // IQN (networks.py:264-292): cosine embedding -> linear -> relu -> * state embedding -> value head.
 int forward_heads_iqn(dz_learner* l, const Pass* passes, int np, int nimg, const float* const* taus, bool keep_E0, void* stream) {
   const Dims& d = l->d;
@@ -1323,17 +1455,20 @@ int forward_heads_iqn(dz_learner* l, const Pass* passes, int np, int nimg, const
     DZ_LAUNCH(iqn_cos_kernel, (unsigned)ceil_div(rows * c.latent_dim, 256), 256, 0, stream, taus[i], l->cosf[passes[i].head],
               rows, c.latent_dim);
   }
-  for (int i = 0; i < np; ++i) {
-    int hp = passes[i].head;
-    GemmProblem p = zero_problem();
-    p.a_mode = A_PLAIN; p.A = l->cosf[hp]; p.lda = c.latent_dim; p.M = nimg * l->n_head[hp]; p.K = c.latent_dim;
-    p.B = passes[i].params + L.off("embed/w"); p.N = d.feat; p.ldb = d.feat; p.ldc = d.feat;
-    p.bias = passes[i].params + L.off("embed/b"); p.relu = 1;
-    p.mul = l->act3[passes[i].set]; p.mul_div = l->n_head[hp];
-    p.C = l->hi[hp]; p.C2 = (keep_E0 && hp == 0) ? l->E0 : nullptr;
-    gb.p[i] = p;
+  const bool packed = l->pk_on && nimg == l->B && np == 3;
+  if (!packed) {
+    for (int i = 0; i < np; ++i) {
+      int hp = passes[i].head;
+      GemmProblem p = zero_problem();
+      p.a_mode = A_PLAIN; p.A = l->cosf[hp]; p.lda = c.latent_dim; p.M = nimg * l->n_head[hp]; p.K = c.latent_dim;
+      p.B = passes[i].params + L.off("embed/w"); p.N = d.feat; p.ldb = d.feat; p.ldc = d.feat;
+      p.bias = passes[i].params + L.off("embed/b"); p.relu = 1;
+      p.mul = l->act3[passes[i].set]; p.mul_div = l->n_head[hp];
+      p.C = l->hi[hp]; p.C2 = (keep_E0 && hp == 0) ? l->E0 : nullptr;
+      gb.p[i] = p;
+    }
+    DZ_TRY(run_nn("iqn_embed_fwd", gb, false, stream));
   }
-  DZ_TRY(run_nn("iqn_embed_fwd", gb, false, stream));
   for (int i = 0; i < np; ++i) {
     int hp = passes[i].head;
     GemmProblem p = zero_problem();
@@ -1343,7 +1478,11 @@ int forward_heads_iqn(dz_learner* l, const Pass* passes, int np, int nimg, const
     gb.p[i] = p;
   }
   // M can be small when acting (1 x tau_samples_policy rows): same kernel family handles it
-  DZ_TRY(run_nn("iqn_fc1_fwd", gb, false, stream));
+  if (packed) {
+    DZ_TRY(iqn_embed_fc1_forward_packed(l, passes, gb, keep_E0, stream));
+  } else {
+    DZ_TRY(run_nn("iqn_fc1_fwd", gb, false, stream));
+  }
   for (int i = 0; i < np; ++i) {
     int hp = passes[i].head;
     GemmProblem p = zero_problem();
@@ -1600,6 +1739,37 @@ int backward_iqn(dz_learner* l, void* stream) {
     gb.p[0] = p;
     DZ_TRY(run_nt("iqn_head_dgrad", gb, false, stream));
   }
+  if (l->pk_on) {
+    // dh1 in both operand orientations, then the two big contractions on the tcgen05 kernel
+    PackBatch pb;
+    memset(&pb, 0, sizeof(pb));
+    DZ_TRY(pk_add_job(pb, l->dh1[0], 512, 0, 512, M, l->pk_dh1T.rows_pad, l->pk_dh1T.red_pad, -1, l->pk_dh1T.hi, l->pk_dh1T.lo));
+    DZ_TRY(pk_add_job(pb, l->dh1[0], 512, 1, M, 512, l->pk_dh1.rows_pad, l->pk_dh1.red_pad, -1, l->pk_dh1.hi, l->pk_dh1.lo));
+    DZ_TRY(launch_pack("iqn_fc1_pack_bwd", pb, stream));
+    PkBatch kb;
+    memset(&kb, 0, sizeof(kb));
+    kb.n = 1;
+    kb.run_kb = 4;
+    {  // fc1 wgrad: [feat + 1 (bias row), 512] = hi0^T(+ones) * dh1, reduction over the M rows, split partials
+      PkProblem& p = kb.p[0];
+      p.A = PkOperand{l->pk_actT.hi, l->pk_actT.lo, l->pk_actT.rows_pad / 8};
+      p.B = PkOperand{l->pk_dh1T.hi, l->pk_dh1T.lo, l->pk_dh1T.rows_pad / 8};
+      p.MI = d.feat + 1; p.NJ = 512; p.nkb = l->pk_actT.red_pad / kPkKB;
+      p.sc_i = 512; p.sc_j = 1; p.splits = l->pk_wgrad_splits; p.split_stride = (long long)(d.feat + 1) * 512;
+      p.C = l->pk_wgrad_partial;
+      DZ_TRY(launch_pgemm("iqn_fc1_wgrad", kb, fork_side(l, stream)));
+      fb.f[fb.n++] = FinishTN{p.C, p.splits, p.split_stride, d.feat, 512, G + L.off("fc1/w"), nullptr, G + L.off("fc1/b"), nullptr, nullptr, nullptr};
+    }
+    {  // dHI[m,k] = sum_n dh1[m,n] W[k,n]
+      PkProblem& p = kb.p[0];
+      memset(&p, 0, sizeof(p));   // (run_kb stays 4)
+      p.A = PkOperand{l->pk_dh1.hi, l->pk_dh1.lo, l->pk_dh1.rows_pad / 8};
+      p.B = PkOperand{l->pk_w.hi, l->pk_w.lo, l->pk_w.rows_pad / 8};
+      p.MI = M; p.NJ = d.feat; p.nkb = l->pk_dh1.red_pad / kPkKB;
+      p.sc_i = d.feat; p.sc_j = 1; p.splits = 1; p.split_stride = 0; p.C = l->dhi;
+      DZ_TRY(launch_pgemm("iqn_fc1_dgrad", kb, stream));
+    }
+  } else {
   {  // fc1 wgrad (reduction over M rows, no split: 400 tiles already)
     GemmProblem p = zero_problem();
     p.a_mode = A_PLAIN; p.A = l->hi[0]; p.lda = d.feat; p.M = M; p.K = d.feat;
@@ -1615,6 +1785,7 @@ int backward_iqn(dz_learner* l, void* stream) {
     gb.p[0] = p;
     DZ_TRY(run_nt("iqn_fc1_dgrad", gb, false, stream));
   }
+  }
   DZ_LAUNCH(iqn_hadamard_bwd_kernel, (unsigned)ceil_div((long long)B * d.feat, 256), 256, 0, stream, l->dhi, l->E0, l->act3[0],
             l->dact3, B, N, d.feat);
   {  // embed wgrad: [latent, feat] = cos^T * dE
@@ -1628,7 +1799,8 @@ int backward_iqn(dz_learner* l, void* stream) {
     DZ_TRY(run_tn("iqn_embed_wgrad", gb, fork_side(l, stream)));
     fb.f[fb.n++] = FinishTN{p.C, splits, p.split_stride, c.latent_dim, d.feat, G + L.off("embed/w"), nullptr, p.Cb, nullptr, nullptr, nullptr};
   }
-  long long mx = std::max<long long>((long long)513 * d.out, (long long)(c.latent_dim + 1) * d.feat);
+  long long mx = 0;
+  for (int q = 0; q < fb.n; ++q) mx = std::max<long long>(mx, (long long)(fb.f[q].K + 1) * fb.f[q].N);
   dim3 grid((unsigned)ceil_div(mx, 256), fb.n);
   DZ_LAUNCH(finish_tn_kernel, grid, 256, 0, (l->side && l->side_dirty ? (void*)l->side : stream), fb);
   return DZ_OK;
@@ -1747,6 +1919,7 @@ int dz_learner_plan_query(const dz_learner_config* cfg, dz_learner_plan* out) {
   out->param_count = tmp.lay.total;
   out->num_tensors = (int32_t)tmp.lay.t.size();
   out->opt_state_floats = 2 * tmp.lay.total;
+  read_env();
   out->workspace_bytes = carve(&tmp, nullptr);
   out->noise_floats = cfg->kind == DZ_RAINBOW ? 3 * noise_stride(*cfg, tmp.d) : 0;
   out->tau_floats = cfg->kind == DZ_IQN
@@ -1771,8 +1944,7 @@ int dz_learner_create(const dz_learner_config* cfg, const dz_learner_buffers* bu
   DZ_TRY(validate(*cfg));
   if (!buf->d_online || !buf->d_target || !buf->d_grads || !buf->d_opt_state || !buf->d_workspace || !buf->d_counters)
     return fail(DZ_EINVAL, "all learner buffers are required");
-  g_use_tc = getenv("DZ_TC") != nullptr && std::string(getenv("DZ_TC")) != "0";
-  g_tc_layers = getenv("DZ_TC") ? getenv("DZ_TC") : "";
+  read_env();
   dz_learner* l = new dz_learner();
   l->cfg = *cfg;
   l->buf = *buf;
@@ -1788,6 +1960,18 @@ int dz_learner_create(const dz_learner_config* cfg, const dz_learner_buffers* bu
       l->side = nullptr;
       cudaGetLastError();
     }
+  }
+  if (l->pk_on) {
+    // fused epilogues only write the valid region of these images: zero the padding once, and set the constant
+    // row of ones (bias-gradient row) of the transposed activation image
+    for (int p = 0; p < 3; ++p) {
+      cudaMemset(l->pk_act[p].hi, 0, pk_image_floats(l->pk_act[p].rows_pad, l->pk_act[p].red_pad) * sizeof(float));
+      cudaMemset(l->pk_act[p].lo, 0, pk_image_floats(l->pk_act[p].rows_pad, l->pk_act[p].red_pad) * sizeof(float));
+    }
+    cudaMemset(l->pk_actT.hi, 0, pk_image_floats(l->pk_actT.rows_pad, l->pk_actT.red_pad) * sizeof(float));
+    cudaMemset(l->pk_actT.lo, 0, pk_image_floats(l->pk_actT.rows_pad, l->pk_actT.red_pad) * sizeof(float));
+    int rc = pk_set_ones_row(l->pk_actT.hi, l->pk_actT.rows_pad, l->d.feat, l->B * l->n_head[0], nullptr);
+    if (rc != DZ_OK || cudaDeviceSynchronize() != cudaSuccess) { delete l; return rc != DZ_OK ? rc : fail(DZ_ECUDA, "packed image init"); }
   }
   cudaError_t e = cudaMemset(l->ticket, 0, 16);
   if (e != cudaSuccess) { delete l; return fail(DZ_ECUDA, "cudaMemset: %s", cudaGetErrorString(e)); }
@@ -1866,6 +2050,23 @@ int dz_learner_q_values(dz_learner* l, const uint8_t* d_obs, const float* d_taus
 int dz_learner_sync_target(dz_learner* l, void* stream) {
   DZ_CUDA_OK(cudaMemcpyAsync(l->buf.d_target, l->buf.d_online, l->lay.total * sizeof(float), cudaMemcpyDeviceToDevice,
                              (cudaStream_t)stream));
+  return DZ_OK;
+}
+
+// Test hook: device pointer + element count of an internal activation / gradient buffer (tests and tools only).
+int dz_test_learner_buffer(dz_learner* l, const char* name, float** d_ptr, int64_t* count) {
+  const std::string n = name;
+  const int64_t rows0 = (int64_t)l->B * l->n_head[0];
+  if (n == "act3") { *d_ptr = l->act3[0]; *count = (int64_t)l->B * l->d.feat; }
+  else if (n == "h1") { *d_ptr = l->h1[0][0]; *count = rows0 * 512; }
+  else if (n == "dh1") { *d_ptr = l->dh1[0]; *count = rows0 * 512; }
+  else if (n == "iqn_hi") {
+    if (l->pk_on) return fail(DZ_EINVAL, "iqn_hi is not materialised on the packed tcgen05 path (DZ_PK_IQN=0 keeps it)");
+    *d_ptr = l->hi[0]; *count = l->hi[0] ? rows0 * l->d.feat : 0;
+  }
+  else if (n == "iqn_dhi") { *d_ptr = l->dhi; *count = l->dhi ? rows0 * l->d.feat : 0; }
+  else return fail(DZ_EINVAL, "unknown buffer '%s'", name);
+  if (!*d_ptr) return fail(DZ_EINVAL, "buffer '%s' is not used by this agent kind", name);
   return DZ_OK;
 }
 

@@ -302,6 +302,20 @@ int dz_test_tc_gemm(const float* d_A, int32_t a_na, int32_t a_nb, int32_t a_ld, 
                     int32_t NJ, int32_t R, int64_t sc_i, int64_t sc_j, int32_t splits, int64_t split_stride,
                     int32_t tile_n, void* stream);
 
+/* Self-test of the packed-operand tcgen05 GEMM (csrc/dz_tcp.cuh; the IQN 3136->512 layer's kernels): packs
+ * A (a_rows x red) and B (b_rows x red) from plain fp32 matrices (x_red_contig = 1: element (row, r) at
+ * x[row*ld + r]; 0: at x[r*ld + row]) into hi/lo TF32 tile images inside d_work (dz_test_tc_pgemm_work floats),
+ * then D[i,j] = sum_r A(i,r) B(j,r).  a_ones_row = a_rows appends a row of ones to A (bias-gradient row), -1: none.
+ * splits == 1: + d_bias[j] and ReLU are applied if given; otherwise raw partials at d_C + s*split_stride. */
+/* Device pointer + element count of an internal learner buffer ("act3", "h1", "dh1", "iqn_hi", "iqn_dhi");
+ * tests/tools only. */
+int dz_test_learner_buffer(dz_learner* l, const char* name, float** d_ptr, int64_t* count);
+int64_t dz_test_tc_pgemm_work(int32_t a_rows, int32_t b_rows, int32_t red);
+int dz_test_tc_pgemm(const float* d_A, int32_t a_rows, int32_t a_ld, int32_t a_red_contig, const float* d_B,
+                     int32_t b_rows, int32_t b_ld, int32_t b_red_contig, int32_t red, int32_t a_ones_row,
+                     float* d_work, float* d_C, int64_t sc_i, int64_t sc_j, int32_t splits, int64_t split_stride,
+                     const float* d_bias, int32_t relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

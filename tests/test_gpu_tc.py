@@ -90,3 +90,73 @@ def test_accuracy_is_fp32_grade_not_tf32_grade():
   split8 = rel(run_tc(A, 1, B, 1, 128, 64, 1024, splits=8), want)
   assert one_run < 4e-6, one_run
   assert split8 < 2 * max(rel(fp32, want), 2e-7), (split8, rel(fp32, want))
+
+
+# ---- packed-operand kernel (dz_tcp.cuh): the IQN 3136 -> 512 layer's shapes -----------------------------------
+
+def run_pgemm(A_src, a_contig, B_src, b_contig, a_rows, b_rows, red, splits=1, ones_row=False, bias=None, relu=False,
+              transpose_out=False):
+  from dqn_zoo_b200 import _lib
+  dev = 'cuda'
+  dA = torch.as_tensor(A_src, device=dev).contiguous()
+  dB = torch.as_tensor(B_src, device=dev).contiguous()
+  MI = a_rows + (1 if ones_row else 0)
+  work = torch.empty(int(_lib.lib.dz_test_tc_pgemm_work(a_rows, b_rows, red)), dtype=torch.float32, device=dev)
+  shape = (splits, b_rows, MI) if transpose_out else (splits, MI, b_rows)
+  out = torch.full(shape, float('nan'), dtype=torch.float32, device=dev)
+  sc_i, sc_j = (1, MI) if transpose_out else (b_rows, 1)
+  db = None if bias is None else torch.as_tensor(bias, device=dev).contiguous()
+  _lib.call('dz_test_tc_pgemm', dA.data_ptr(), a_rows, dA.shape[1], a_contig, dB.data_ptr(), b_rows, dB.shape[1], b_contig,
+            red, a_rows if ones_row else -1, work.data_ptr(), out.data_ptr(), sc_i, sc_j, splits, MI * b_rows,
+            0 if db is None else db.data_ptr(), int(relu), torch.cuda.current_stream().cuda_stream)
+  torch.cuda.synchronize()
+  res = out.sum(0).cpu().numpy().astype(np.float64)
+  return res.T if transpose_out else res
+
+
+@pytest.mark.parametrize('a_rows,b_rows,red,splits', [(128, 256, 16, 1), (128, 256, 128, 1), (128, 256, 272, 1),
+                                                      (300, 512, 1000, 1), (2048, 512, 3136, 3), (200, 70, 100, 2),
+                                                      (384, 3136, 512, 1)])
+def test_packed_gemm_all_source_orientations(a_rows, b_rows, red, splits):
+  rs = np.random.RandomState(a_rows + b_rows + red)
+  Am = rs.standard_normal((a_rows, red)).astype(np.float32)
+  Bm = rs.standard_normal((b_rows, red)).astype(np.float32)
+  want = Am.astype(np.float64) @ Bm.astype(np.float64).T
+  scale = np.sqrt(red)
+  for a_contig in (1, 0):
+    for b_contig in (1, 0):
+      got = run_pgemm(Am if a_contig else np.ascontiguousarray(Am.T), a_contig, Bm if b_contig else np.ascontiguousarray(Bm.T),
+                      b_contig, a_rows, b_rows, red, splits)
+      assert np.isfinite(got).all()
+      assert rel(got, want) < 2e-6, (a_contig, b_contig, rel(got, want))
+      assert np.abs(got - want).max() / scale < 2e-5
+  got = run_pgemm(Am, 1, Bm, 1, a_rows, b_rows, red, splits, transpose_out=True)
+  assert rel(got, want) < 2e-6
+
+
+def test_packed_gemm_bias_relu_and_ones_row():
+  rs = np.random.RandomState(5)
+  a_rows, b_rows, red = 333, 512, 2048
+  Am = rs.standard_normal((a_rows, red)).astype(np.float32)
+  Bm = rs.standard_normal((b_rows, red)).astype(np.float32)
+  bias = rs.standard_normal(b_rows).astype(np.float32)
+  want = np.maximum(Am.astype(np.float64) @ Bm.astype(np.float64).T + bias, 0.0)
+  got = run_pgemm(Am, 1, Bm, 1, a_rows, b_rows, red, 1, bias=bias, relu=True)
+  assert np.abs(got - want).max() < 2e-4 and rel(got, want) < 2e-6
+  # weight-gradient form: sources [red][rows], an appended row of ones yields the column sums (bias gradient)
+  got = run_pgemm(np.ascontiguousarray(Am.T), 0, np.ascontiguousarray(Bm.T), 0, a_rows, b_rows, red, 5, ones_row=True)
+  want = np.concatenate([Am.astype(np.float64) @ Bm.astype(np.float64).T, Bm.astype(np.float64).sum(1)[None]], 0)
+  assert got.shape == want.shape and rel(got, want) < 2e-6
+
+
+def test_packed_gemm_sign_consistent_sum_has_no_truncation_bias():
+  """All-positive operands: a round-towards-zero accumulator run over the whole reduction would lose ~2e-8 per
+  accumulation (3136/8*3 of them); draining every 128 elements keeps the result at fp32 grade."""
+  rs = np.random.RandomState(9)
+  Am = rs.uniform(0.5, 1.5, size=(256, 3136)).astype(np.float32)
+  Bm = rs.uniform(0.5, 1.5, size=(256, 3136)).astype(np.float32)
+  want = Am.astype(np.float64) @ Bm.astype(np.float64).T
+  got = run_pgemm(Am, 1, Bm, 1, 256, 256, 3136, 1)
+  bias = ((got - want) / want).mean()
+  assert abs(bias) < 1.5e-6, bias
+  assert np.abs((got - want) / want).max() < 3e-6
