@@ -285,6 +285,58 @@ __global__ void __launch_bounds__(256) iqn_hadamard_bwd_kernel(float* __restrict
   dfeat[i] = f > 0.f ? acc : 0.f;  // F is the post-ReLU conv3 output: mask for the conv3 pre-activation
 }
 
+// Packed variant for the tcgen05 path: same math, but dE is written ONLY as the hi/lo TF32 tile images of the
+// transposed operand (rows k, reduction m = b*N + n; layout in dz_tcp.cuh) that the embedding weight-gradient GEMM
+// consumes.  One block = one sample b x 64 features; requires N == 64 and D % 64 == 0.
+__global__ void __launch_bounds__(256) iqn_hadamard_bwd_packed_kernel(const float* __restrict__ dHI, const float* __restrict__ E,
+                                                                      const float* __restrict__ F, float* __restrict__ dfeat,
+                                                                      float* __restrict__ img_hi, float* __restrict__ img_lo,
+                                                                      int rg_total, int D) {
+  constexpr int N = 64;
+  __shared__ float tile[64][65];
+  __shared__ float red[16][64];
+  const int b = blockIdx.y, k0 = blockIdx.x * 64, tid = threadIdx.x;
+  const int a = tid >> 4, k4 = (tid & 15) * 4;
+  const float4 f = *reinterpret_cast<const float4*>(F + (long long)b * D + k0 + k4);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int n = a + 16 * q;
+    const long long j = ((long long)b * N + n) * D + k0 + k4;
+    const float4 g = *reinterpret_cast<const float4*>(dHI + j);
+    const float4 e = *reinterpret_cast<const float4*>(E + j);
+    acc.x = fmaf(g.x, e.x, acc.x); acc.y = fmaf(g.y, e.y, acc.y); acc.z = fmaf(g.z, e.z, acc.z); acc.w = fmaf(g.w, e.w, acc.w);
+    tile[n][k4 + 0] = e.x > 0.f ? g.x * f.x : 0.f;
+    tile[n][k4 + 1] = e.y > 0.f ? g.y * f.y : 0.f;
+    tile[n][k4 + 2] = e.z > 0.f ? g.z * f.z : 0.f;
+    tile[n][k4 + 3] = e.w > 0.f ? g.w * f.w : 0.f;
+  }
+  red[a][k4 + 0] = acc.x; red[a][k4 + 1] = acc.y; red[a][k4 + 2] = acc.z; red[a][k4 + 3] = acc.w;
+  __syncthreads();
+  if (tid < 64) {
+    float sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) sum += red[r][tid];
+    const long long i = (long long)b * D + k0 + tid;
+    dfeat[i] = F[i] > 0.f ? sum : 0.f;   // F is the post-ReLU conv3 output: mask for the conv3 pre-activation
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int id = tid + q * 256;
+    const int r = id & 7, c = (id >> 3) & 3, rg = (id >> 5) & 7, kb = id >> 8;
+    const int k = k0 + rg * 8 + r, ml = kb * 16 + c * 4;
+    float4 x = make_float4(tile[ml][rg * 8 + r], tile[ml + 1][rg * 8 + r], tile[ml + 2][rg * 8 + r], tile[ml + 3][rg * 8 + r]);
+    float4 h, l;
+    h.x = tc::rn_tf32(x.x); l.x = tc::rn_tf32(x.x - h.x);
+    h.y = tc::rn_tf32(x.y); l.y = tc::rn_tf32(x.y - h.y);
+    h.z = tc::rn_tf32(x.z); l.z = tc::rn_tf32(x.z - h.z);
+    h.w = tc::rn_tf32(x.w); l.w = tc::rn_tf32(x.w - h.w);
+    const long long off = (((((long long)(b * 4 + kb) * rg_total + (k >> 3)) << 2) + c) << 5) + (k & 7) * 4;
+    *reinterpret_cast<float4*>(img_hi + off) = h;
+    *reinterpret_cast<float4*>(img_lo + off) = l;
+  }
+}
+
 // ---- randomness --------------------------------------------------------------------------------
 
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
@@ -799,7 +851,9 @@ struct dz_learner {
   // packed-operand tcgen05 path of the IQN 3136->512 layer (dz_tcp.cuh): hi/lo tile images + split partials
   bool pk_on;
   struct PkImg { float* hi; float* lo; int rows_pad, red_pad; };
-  PkImg pk_act[3], pk_wT[2], pk_w, pk_actT, pk_dh1T, pk_dh1, pk_cos[3], pk_weT[2];
+  PkImg pk_act[3], pk_wT[2], pk_w, pk_actT, pk_dh1T, pk_dh1, pk_cos[3], pk_weT[2], pk_dET, pk_cosT;
+  bool pk_embed_bwd;
+  int pk_embed_wgrad_splits;
   float *pk_fwd_partial, *pk_wgrad_partial;
   int pk_fwd_splits, pk_wgrad_splits;
   // second stream for work that is off the critical path of the backward pass (weight gradients, priority
@@ -877,7 +931,7 @@ int64_t carve(dz_learner* l, char* base) {
   l->tn_partial[1] = w.take<float>((int64_t)32 * 513 * 64);
   l->tn_partial[2] = w.take<float>((int64_t)32 * 577 * 64);
   l->tn_partial[3] = iqn ? w.take<float>((int64_t)16 * (c.latent_dim + 1) * d.feat + 16 * 513 * 64) : nullptr;
-  l->pk_on = false;
+  l->pk_on = false; l->pk_embed_bwd = false;
   if (iqn && g_pk_iqn && rows0 >= 1024 && (int64_t)B * nh[1] >= 1024 && (int64_t)B * nh[2] >= 1024 && d.feat % 16 == 0 &&
       c.latent_dim <= 128 && rows0 % 4 == 0 && ((int64_t)B * nh[1]) % 4 == 0 && ((int64_t)B * nh[2]) % 4 == 0) {
     l->pk_on = true;
@@ -898,6 +952,12 @@ int64_t carve(dz_learner* l, char* base) {
     for (int p = 0; p < 3; ++p) img(l->pk_cos[p], (int64_t)B * nh[p], c.latent_dim, 128);
     img(l->pk_weT[0], d.feat, c.latent_dim, 256);
     img(l->pk_weT[1], d.feat, c.latent_dim, 256);
+    l->pk_embed_bwd = nh[0] == 64 && d.feat % 64 == 0;
+    if (l->pk_embed_bwd) {
+      img(l->pk_dET, d.feat, rows0, 128);
+      img(l->pk_cosT, c.latent_dim + 1, rows0, 256);
+      l->pk_embed_wgrad_splits = pick_splits(l->pk_dET.rows_pad / 128, l->pk_dET.red_pad / kPkKB, 8);
+    }
     l->pk_fwd_splits = pick_splits(tiles, l->pk_act[0].red_pad / kPkKB, 6);
     l->pk_wgrad_splits = pick_splits((int64_t)l->pk_actT.rows_pad / 128 * 2, l->pk_actT.red_pad / kPkKB, 8);
     int64_t fwd_rows = (int64_t)B * (nh[0] + nh[1] + nh[2]);
@@ -1745,6 +1805,9 @@ int backward_iqn(dz_learner* l, void* stream) {
     memset(&pb, 0, sizeof(pb));
     DZ_TRY(pk_add_job(pb, l->dh1[0], 512, 0, 512, M, l->pk_dh1T.rows_pad, l->pk_dh1T.red_pad, -1, l->pk_dh1T.hi, l->pk_dh1T.lo));
     DZ_TRY(pk_add_job(pb, l->dh1[0], 512, 1, M, 512, l->pk_dh1.rows_pad, l->pk_dh1.red_pad, -1, l->pk_dh1.hi, l->pk_dh1.lo));
+    if (l->pk_embed_bwd)   // cos^T plus a row of ones (bias gradient) for the embedding weight gradient
+      DZ_TRY(pk_add_job(pb, l->cosf[0], c.latent_dim, 0, c.latent_dim, M, l->pk_cosT.rows_pad, l->pk_cosT.red_pad, c.latent_dim,
+                        l->pk_cosT.hi, l->pk_cosT.lo));
     DZ_TRY(launch_pack("iqn_fc1_pack_bwd", pb, stream));
     PkBatch kb;
     memset(&kb, 0, sizeof(kb));
@@ -1786,18 +1849,37 @@ int backward_iqn(dz_learner* l, void* stream) {
     DZ_TRY(run_nt("iqn_fc1_dgrad", gb, false, stream));
   }
   }
+  if (l->pk_embed_bwd) {
+    dim3 hgrid((unsigned)(d.feat / 64), (unsigned)B);
+    DZ_LAUNCH(iqn_hadamard_bwd_packed_kernel, hgrid, 256, 0, stream, l->dhi, l->E0, l->act3[0], l->dact3, l->pk_dET.hi,
+              l->pk_dET.lo, l->pk_dET.rows_pad / 8, d.feat);
+    // embed wgrad: [feat, latent + 1 (bias column)] = dE^T * [cos | 1], stored transposed into the [latent + 1, feat] partials
+    PkBatch kb;
+    memset(&kb, 0, sizeof(kb));
+    kb.n = 1;
+    kb.run_kb = 4;
+    PkProblem& p = kb.p[0];
+    p.A = PkOperand{l->pk_dET.hi, l->pk_dET.lo, l->pk_dET.rows_pad / 8};
+    p.B = PkOperand{l->pk_cosT.hi, l->pk_cosT.lo, l->pk_cosT.rows_pad / 8};
+    p.MI = d.feat; p.NJ = c.latent_dim + 1; p.nkb = l->pk_dET.red_pad / kPkKB;
+    p.sc_i = 1; p.sc_j = d.feat; p.splits = l->pk_embed_wgrad_splits; p.split_stride = (long long)(c.latent_dim + 1) * d.feat;
+    p.C = part_embed;
+    DZ_TRY(launch_pgemm("iqn_embed_wgrad", kb, fork_side(l, stream)));
+    fb.f[fb.n++] = FinishTN{p.C, p.splits, p.split_stride, c.latent_dim, d.feat, G + L.off("embed/w"), nullptr, G + L.off("embed/b"), nullptr, nullptr, nullptr};
+  } else {
   DZ_LAUNCH(iqn_hadamard_bwd_kernel, (unsigned)ceil_div((long long)B * d.feat, 256), 256, 0, stream, l->dhi, l->E0, l->act3[0],
-            l->dact3, B, N, d.feat);
-  {  // embed wgrad: [latent, feat] = cos^T * dE
-    GemmProblem p = zero_problem();
-    p.a_mode = A_PLAIN; p.A = l->cosf[0]; p.lda = c.latent_dim; p.M = M; p.K = c.latent_dim;
-    p.B = l->dhi; p.N = d.feat; p.ldb = d.feat; p.ldc = d.feat;
-    p.Cb = G + L.off("embed/b");
-    int splits = (int)std::min<int64_t>(16, ceil_div(M, 64));
-    p.splits = splits; p.split_stride = (long long)(c.latent_dim + 1) * d.feat; p.C = part_embed;
-    gb.p[0] = p;
-    DZ_TRY(run_tn("iqn_embed_wgrad", gb, fork_side(l, stream)));
-    fb.f[fb.n++] = FinishTN{p.C, splits, p.split_stride, c.latent_dim, d.feat, G + L.off("embed/w"), nullptr, p.Cb, nullptr, nullptr, nullptr};
+              l->dact3, B, N, d.feat);
+    {  // embed wgrad: [latent, feat] = cos^T * dE
+      GemmProblem p = zero_problem();
+      p.a_mode = A_PLAIN; p.A = l->cosf[0]; p.lda = c.latent_dim; p.M = M; p.K = c.latent_dim;
+      p.B = l->dhi; p.N = d.feat; p.ldb = d.feat; p.ldc = d.feat;
+      p.Cb = G + L.off("embed/b");
+      int splits = (int)std::min<int64_t>(16, ceil_div(M, 64));
+      p.splits = splits; p.split_stride = (long long)(c.latent_dim + 1) * d.feat; p.C = part_embed;
+      gb.p[0] = p;
+      DZ_TRY(run_tn("iqn_embed_wgrad", gb, fork_side(l, stream)));
+      fb.f[fb.n++] = FinishTN{p.C, splits, p.split_stride, c.latent_dim, d.feat, G + L.off("embed/w"), nullptr, p.Cb, nullptr, nullptr, nullptr};
+    }
   }
   long long mx = 0;
   for (int q = 0; q < fb.n; ++q) mx = std::max<long long>(mx, (long long)(fb.f[q].K + 1) * fb.f[q].N);
@@ -1970,6 +2052,10 @@ int dz_learner_create(const dz_learner_config* cfg, const dz_learner_buffers* bu
     }
     cudaMemset(l->pk_actT.hi, 0, pk_image_floats(l->pk_actT.rows_pad, l->pk_actT.red_pad) * sizeof(float));
     cudaMemset(l->pk_actT.lo, 0, pk_image_floats(l->pk_actT.rows_pad, l->pk_actT.red_pad) * sizeof(float));
+    if (l->pk_embed_bwd) {
+      cudaMemset(l->pk_dET.hi, 0, pk_image_floats(l->pk_dET.rows_pad, l->pk_dET.red_pad) * sizeof(float));
+      cudaMemset(l->pk_dET.lo, 0, pk_image_floats(l->pk_dET.rows_pad, l->pk_dET.red_pad) * sizeof(float));
+    }
     int rc = pk_set_ones_row(l->pk_actT.hi, l->pk_actT.rows_pad, l->d.feat, l->B * l->n_head[0], nullptr);
     if (rc != DZ_OK || cudaDeviceSynchronize() != cudaSuccess) { delete l; return rc != DZ_OK ? rc : fail(DZ_ECUDA, "packed image init"); }
   }
