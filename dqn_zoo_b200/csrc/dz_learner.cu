@@ -151,6 +151,30 @@ struct FinishNNBatch { FinishNN f[kMaxProblems]; int n; };
 __global__ void __launch_bounds__(256) finish_nn_kernel(const __grid_constant__ FinishNNBatch b) {
   const FinishNN& f = b.f[blockIdx.y];
   long long total = (long long)f.M * f.N;
+  if ((f.N & 3) == 0 && ((reinterpret_cast<uintptr_t>(f.partial) | reinterpret_cast<uintptr_t>(f.out) | (uintptr_t)(f.stride * 4)) & 15) == 0) {
+    // 16-byte path (every layer except the odd-width heads): same per-element order of additions
+    const long long total4 = total >> 2;
+    for (long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i4 < total4; i4 += (long long)gridDim.x * blockDim.x) {
+      const long long i = i4 << 2;
+      const int n = (int)(i % f.N);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < f.splits; ++k) {
+        const float4 x = *reinterpret_cast<const float4*>(f.partial + k * f.stride + i);
+        v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+      }
+      if (f.bias) {
+        if (f.bias_shared) { const float s = f.bias[0]; v.x += s; v.y += s; v.z += s; v.w += s; }
+        else { v.x += f.bias[n]; v.y += f.bias[n + 1]; v.z += f.bias[n + 2]; v.w += f.bias[n + 3]; }
+      }
+      if (f.dual && f.bias2) {
+        v.x = fmaf(f.bias2[n], f.c_scale[n], v.x); v.y = fmaf(f.bias2[n + 1], f.c_scale[n + 1], v.y);
+        v.z = fmaf(f.bias2[n + 2], f.c_scale[n + 2], v.z); v.w = fmaf(f.bias2[n + 3], f.c_scale[n + 3], v.w);
+      }
+      if (f.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      *reinterpret_cast<float4*>(f.out + i) = v;
+    }
+    return;
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int n = (int)(i % f.N);
     float v = 0.f;
@@ -172,6 +196,22 @@ __global__ void __launch_bounds__(256) finish_tn_kernel(const __grid_constant__ 
   const FinishTN& f = b.f[blockIdx.y];
   int Kext = f.K + ((f.Cb || f.Cb2) ? 1 : 0);
   long long total = (long long)Kext * f.N;
+  if ((f.N & 3) == 0 && !f.C2 && !f.Cb2 && f.C &&
+      ((reinterpret_cast<uintptr_t>(f.partial) | reinterpret_cast<uintptr_t>(f.C) | reinterpret_cast<uintptr_t>(f.Cb) | (uintptr_t)(f.stride * 4)) & 15) == 0) {
+    const long long total4 = total >> 2;
+    for (long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i4 < total4; i4 += (long long)gridDim.x * blockDim.x) {
+      const long long i = i4 << 2;
+      const int k = (int)(i / f.N), n = (int)(i % f.N);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < f.splits; ++s) {
+        const float4 x = *reinterpret_cast<const float4*>(f.partial + s * f.stride + i);
+        v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+      }
+      if (k < f.K) *reinterpret_cast<float4*>(f.C + i) = v;
+      else if (f.Cb) *reinterpret_cast<float4*>(f.Cb + n) = v;
+    }
+    return;
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int k = (int)(i / f.N), n = (int)(i % f.N);
     float v = 0.f;
@@ -258,6 +298,70 @@ __global__ void sum_to_scalar_kernel(const float* __restrict__ v, int n, float* 
 }
 
 // ---- IQN helpers -------------------------------------------------------------------------------
+
+// IQN value head at training size (networks.py:285-287): out[m, a] = sum_k h1[m, k] W[k, a] + b[a] with
+// M = batch * tau_samples rows (thousands), K = 512 and only num_actions (<= 18) columns.  A tiled GEMM wastes its
+// N tile here; instead one warp owns one row: coalesced float4 reads of the row, W^T resident in shared memory,
+// A warp reductions.  Up to three applies (blockIdx.y) per launch.
+constexpr int kSkinnyMaxN = 18;
+struct SkinnyHead { const float* A[3]; const float* W[3]; const float* bias[3]; float* out[3]; int M[3]; int n; };
+
+__global__ void __launch_bounds__(256) iqn_head_fwd_kernel(const __grid_constant__ SkinnyHead h, int N) {
+  constexpr int K = 512;
+  __shared__ __align__(16) float Ws[kSkinnyMaxN * K];
+  const int q = blockIdx.y;
+  const float* __restrict__ W = h.W[q];
+  for (int i = threadIdx.x; i < K * N; i += 256) {      // W is [K][N]: transpose into Ws[n][k]
+    int k = i / N, n = i - k * N;
+    Ws[n * K + k] = W[i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int m = blockIdx.x * 8 + warp; m < h.M[q]; m += gridDim.x * 8) {
+    const float4* a4 = reinterpret_cast<const float4*>(h.A[q] + (long long)m * K);
+    float4 a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = a4[lane + 32 * i];
+    float mine = 0.f;
+    for (int n = 0; n < N; ++n) {
+      const float4* w4 = reinterpret_cast<const float4*>(Ws + n * K);
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 w = w4[lane + 32 * i];
+        acc = fmaf(a[i].x, w.x, acc); acc = fmaf(a[i].y, w.y, acc); acc = fmaf(a[i].z, w.z, acc); acc = fmaf(a[i].w, w.w, acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == n) mine = acc;
+    }
+    if (lane < N) h.out[q][(long long)m * N + lane] = mine + h.bias[q][lane];
+  }
+}
+
+// Input gradient of the same head: dh1[m, k] = [h1 > 0] * sum_a dout[m, a] W[k, a]  (one thread = 4 consecutive k).
+__global__ void __launch_bounds__(256) iqn_head_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ W,
+                                                             const float* __restrict__ h1, float* __restrict__ dh1, int M, int N) {
+  constexpr int K = 512;
+  __shared__ float Ws[K * kSkinnyMaxN];
+  for (int i = threadIdx.x; i < K * N; i += 256) Ws[i] = W[i];
+  __syncthreads();
+  const long long total = (long long)M * (K / 4);
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int m = (int)(i >> 7), k = (int)(i & 127) * 4;
+    float d[kSkinnyMaxN];
+    for (int n = 0; n < N; ++n) d[n] = dout[(long long)m * N + n];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int n = 0; n < N; ++n) {
+      v.x = fmaf(d[n], Ws[(k + 0) * N + n], v.x);
+      v.y = fmaf(d[n], Ws[(k + 1) * N + n], v.y);
+      v.z = fmaf(d[n], Ws[(k + 2) * N + n], v.z);
+      v.w = fmaf(d[n], Ws[(k + 3) * N + n], v.w);
+    }
+    const float4 h = *reinterpret_cast<const float4*>(h1 + (long long)m * K + k);
+    v.x = h.x > 0.f ? v.x : 0.f; v.y = h.y > 0.f ? v.y : 0.f; v.z = h.z > 0.f ? v.z : 0.f; v.w = h.w > 0.f ? v.w : 0.f;
+    *reinterpret_cast<float4*>(dh1 + (long long)m * K + k) = v;
+  }
+}
 
 // cos(pi * i * tau), i = 1..latent; the product is formed in float32 as in networks.py:277-278.
 __global__ void iqn_cos_kernel(const float* __restrict__ taus, float* __restrict__ out, long long rows, int latent) {
@@ -1264,7 +1368,7 @@ int finish_nn(const GemmBatch& gb, float* const* outs, bool dual, void* stream) 
     long long t = (long long)p.M * p.N;
     mx = t > mx ? t : mx;
   }
-  dim3 grid((unsigned)ceil_div(mx, 256), gb.n);
+  dim3 grid((unsigned)std::min<long long>(ceil_div(mx, 256), 148 * 8), gb.n);   // grid-stride kernels
   DZ_LAUNCH(finish_nn_kernel, grid, 256, 0, stream, fb);
   return DZ_OK;
 }
@@ -1543,6 +1647,21 @@ int forward_heads_iqn(dz_learner* l, const Pass* passes, int np, int nimg, const
   } else {
     DZ_TRY(run_nn("iqn_fc1_fwd", gb, false, stream));
   }
+  if ((long long)nimg * l->n_head[passes[0].head] >= 512 && d.out <= kSkinnyMaxN && np <= 3) {
+    SkinnyHead h;
+    memset(&h, 0, sizeof(h));
+    h.n = np;
+    int maxM = 0;
+    for (int i = 0; i < np; ++i) {
+      int hp = passes[i].head;
+      h.A[i] = l->h1[hp][0]; h.W[i] = passes[i].params + L.off("head/w"); h.bias[i] = passes[i].params + L.off("head/b");
+      h.out[i] = l->out[hp]; h.M[i] = nimg * l->n_head[hp];
+      maxM = std::max(maxM, h.M[i]);
+    }
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div(maxM, 8), 148 * 2), (unsigned)np);
+    DZ_LAUNCH_NAMED("iqn_head_fwd", iqn_head_fwd_kernel, grid, 256, 0, stream, h, d.out);
+    return DZ_OK;
+  }
   for (int i = 0; i < np; ++i) {
     int hp = passes[i].head;
     GemmProblem p = zero_problem();
@@ -1797,7 +1916,12 @@ int backward_iqn(dz_learner* l, void* stream) {
     p.A = l->dout; p.lda = d.out; p.M = M; p.N = d.out; p.K = 512;
     p.B = P + L.off("head/w"); p.ldb = d.out; p.C = l->dh1[0]; p.ldc = 512; p.mask = l->h1[0][0];
     gb.p[0] = p;
-    DZ_TRY(run_nt("iqn_head_dgrad", gb, false, stream));
+    if (M >= 512 && d.out <= kSkinnyMaxN) {
+      DZ_LAUNCH_NAMED("iqn_head_dgrad", iqn_head_dgrad_kernel, (unsigned)std::min<int64_t>(ceil_div((long long)M * 128, 256), 148 * 8),
+                      256, 0, stream, l->dout, P + L.off("head/w"), l->h1[0][0], l->dh1[0], M, d.out);
+    } else {
+      DZ_TRY(run_nt("iqn_head_dgrad", gb, false, stream));
+    }
   }
   if (l->pk_on) {
     // dh1 in both operand orientations, then the two big contractions on the tcgen05 kernel
@@ -1883,7 +2007,7 @@ int backward_iqn(dz_learner* l, void* stream) {
   }
   long long mx = 0;
   for (int q = 0; q < fb.n; ++q) mx = std::max<long long>(mx, (long long)(fb.f[q].K + 1) * fb.f[q].N);
-  dim3 grid((unsigned)ceil_div(mx, 256), fb.n);
+  dim3 grid((unsigned)std::min<long long>(ceil_div(mx, 256), 148 * 8), fb.n);
   DZ_LAUNCH(finish_tn_kernel, grid, 256, 0, (l->side && l->side_dirty ? (void*)l->side : stream), fb);
   return DZ_OK;
 }
@@ -1897,8 +2021,9 @@ int run_optimizer(dz_learner* l, float* user_norm, bool apply, void* stream) {
   if (!apply) return DZ_OK;
   OptArgs o{c.optimizer, c.learning_rate, c.opt_eps, c.rms_decay, c.adam_b1, c.adam_b2, c.max_global_grad_norm,
             l->buf.d_online, l->buf.d_grads, l->buf.d_opt_state, l->buf.d_opt_state + n, n, norm, l->buf.d_counters};
-  if (c.optimizer == DZ_ADAM) DZ_LAUNCH_NAMED("optimizer_kernel", optimizer_kernel<DZ_ADAM>, 148 * 8, 256, 0, stream, o);
-  else DZ_LAUNCH_NAMED("optimizer_kernel", optimizer_kernel<DZ_RMSPROP_CENTERED>, 148 * 8, 256, 0, stream, o);
+  static const int per_sm = getenv("DZ_OPT_BLOCKS") ? atoi(getenv("DZ_OPT_BLOCKS")) : 8;
+  if (c.optimizer == DZ_ADAM) DZ_LAUNCH_NAMED("optimizer_kernel", optimizer_kernel<DZ_ADAM>, 148 * per_sm, 256, 0, stream, o);
+  else DZ_LAUNCH_NAMED("optimizer_kernel", optimizer_kernel<DZ_RMSPROP_CENTERED>, 148 * per_sm, 256, 0, stream, o);
   return DZ_OK;
 }
 
