@@ -323,8 +323,12 @@ def main():
     roofline = {'kernel': name, 'bound': 'tensor', 'achieved': achieved, 'peak': tf_peak, 'unit': 'TFLOP/s',
                 'frac': achieved / tf_peak, 'traffic': traffic, 'alg_flops_per_launch': alg_flops[name],
                 'avg_launch_us': 1e6 * dur_s, 'peak_source': peak_src,
-                'note': 'fp32 FMA kernel today (exact-fp32 products for the 1e-5 parity bar); the peak is the measured dense bf16 '
-                        'tensor throughput, i.e. the fraction states how far this contraction is from the tensor-core roofline'}
+                'note': ('tcgen05 kernel (csrc/dz_tcp.cuh): error-compensated 3xTF32, i.e. three kind::tf32 MMAs per fp32 product '
+                         'to hold the 1e-5 parity bar; `achieved` counts the algorithmic 2*M*N*K only, the peak is the measured '
+                         'dense bf16 tensor throughput')
+                        if name.startswith('iqn_') and os.environ.get('DZ_PK_IQN', '1') != '0' else
+                        ('fp32 FMA kernel today (exact-fp32 products for the 1e-5 parity bar); the peak is the measured dense bf16 '
+                         'tensor throughput, i.e. the fraction states how far this contraction is from the tensor-core roofline')}
   else:
     flops = GFLOP_PER_STEP[args.agent] * 1e9
     achieved = flops / (1e-3 * total_ms / prof_steps) / 1e12

@@ -64,6 +64,11 @@ class UpdateOutputs(C.Structure):
   _fields_ = [('d_loss', vp), ('d_per_example', vp), ('d_priorities', vp), ('d_grad_norm', vp)]
 
 
+class ResampleAxis(C.Structure):   # struct dz_resample_axis
+  _fields_ = [('d_bounds', C.c_void_p), ('d_kk', C.c_void_p), ('ksize', C.c_int32), ('in_size', C.c_int32),
+              ('out_size', C.c_int32)]
+
+
 class LearnIO(C.Structure):
   _fields_ = [('sample_in', SampleInputs), ('sample_out', SampleOutputs), ('d_taus', vp), ('d_noise', vp),
               ('update_out', UpdateOutputs), ('d_max_seen_priority', vp), ('priority_exponent', f64)]
@@ -104,6 +109,8 @@ _SIGNATURES = {
     'dz_test_tc_set_variant': (i32, [i32]),
     'dz_test_tc_gemm': (i32, [vp, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp, i32, i32, i32, i64, i64, i32, i64,
                               i32, vp]),
+    'dz_atari_preprocess': (i32, [vp, vp, i32, vp, vp, vp, vp, i32, vp, i32, vp]),
+    'dz_atari_preprocess_band_rows': (i32, []),
     'dz_test_learner_buffer': (i32, [vp, C.c_char_p, vp, vp]),
     'dz_test_tc_pgemm_work': (i64, [i32, i32, i32]),
     'dz_test_tc_pgemm': (i32, [vp, i32, i32, i32, vp, i32, i32, i32, i32, i32, vp, vp, i64, i64, i32, i64, vp, i32, vp]),

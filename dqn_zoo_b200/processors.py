@@ -1,0 +1,299 @@
+"""Device-backed Atari preprocessing: the `processors.atari()` surface of the reference (dqn_zoo/processors.py:399-505).
+
+Same call protocol — a processor is a callable with `reset()`, fed one raw timestep per frame, returning `None`
+on the frames where the previous action is repeated and a processed timestep otherwise — but the pixel work
+(max-pool of the last two raw frames, rgb2y, PIL bilinear resize, frame stack; processors.py:367-388, 482-501)
+runs in one CUDA kernel (csrc/dz_preprocess.cu) for any number of environment streams at once, and the frame
+stacks live in device memory so that acting (`Learner.q_values`) and replay inserts can consume them without a
+host round trip.  The scalar half (life-loss discount, action-repeat cadence, reward sum/clip, discount product,
+step-type reduction; processors.py:121-215, 254-365) is a per-stream host state machine.
+
+There is no CPU fallback: without the CUDA library the import of `dqn_zoo_b200._lib` fails.
+"""
+
+import ctypes as C
+import math
+from typing import Any, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from dqn_zoo_b200 import _lib
+from dqn_zoo_b200 import parts
+
+StepType = parts.StepType
+
+# processors.py:370 — the third weight is computed, not the literal 0.114
+LUMA = (0.299, 0.587, 1 - (0.299 + 0.587))
+_PRECISION_BITS = 32 - 8 - 2
+
+
+def bilinear_axis(in_size: int, out_size: int) -> Tuple[np.ndarray, np.ndarray, int]:
+  """Window + fixed-point coefficient tables of Pillow's bilinear resampling along one axis.
+
+  (Pillow libImaging/Resample.c precompute_coeffs / normalize_coeffs_8bpc; Pillow is what processors.py:381-386
+  calls.)  Returns bounds int32 [out, 2] = (first, count), kk int32 [out, ksize], ksize."""
+  scale = in_size / out_size
+  filterscale = scale if scale > 1.0 else 1.0
+  support = filterscale                      # bilinear filter support is 1.0
+  ksize = int(math.ceil(support)) * 2 + 1
+  bounds = np.zeros((out_size, 2), np.int32)
+  kk = np.zeros((out_size, ksize), np.int32)
+  inv = 1.0 / filterscale
+  one = float(1 << _PRECISION_BITS)
+  for xx in range(out_size):
+    center = (xx + 0.5) * scale
+    first = max(int(center - support + 0.5), 0)
+    last = min(int(center + support + 0.5), in_size)
+    weights = []
+    total = 0.0
+    for x in range(first, last):
+      t = abs((x - center + 0.5) * inv)
+      w = 1.0 - t if t < 1.0 else 0.0
+      weights.append(w)
+      total += w
+    bounds[xx, 0], bounds[xx, 1] = first, last - first
+    for i, w in enumerate(weights):
+      if total != 0.0:
+        w = w / total
+      kk[xx, i] = int(w * one - 0.5) if w < 0 else int(w * one + 0.5)
+  return bounds, kk, ksize
+
+
+class _Axis:
+  """Device copy of one axis' tables + the C struct pointing at them."""
+
+  def __init__(self, in_size, out_size, device):
+    bounds, kk, ksize = bilinear_axis(in_size, out_size)
+    self.bounds_host = bounds
+    self.d_bounds = torch.from_numpy(bounds).to(device)
+    self.d_kk = torch.from_numpy(kk).to(device)
+    self.c = _lib.ResampleAxis(self.d_bounds.data_ptr(), self.d_kk.data_ptr(), ksize, in_size, out_size)
+
+
+class _Stream:
+  """Scalar state of one environment stream (everything processors.atari() keeps besides pixels)."""
+
+  def __init__(self, repeats):
+    self.repeats = repeats
+    self.reset()
+
+  def reset(self):
+    self.lives = None
+    self.index = (-1) % self.repeats          # FixedPaddedBuffer(length, initial_index=-1), processors.py:142-145
+    self.slots = [None] * self.repeats        # (step_type, reward, discount) or None
+    self.has_frame = [False] * self.repeats
+    self.since_first = None
+    self.should_reset = False
+    self.count = 0                            # frames in the stack deque
+
+
+class BatchedAtariPreprocessor:
+  """`processors.atari()` for `num_streams` independent environment streams sharing one kernel launch per tick."""
+
+  def __init__(self, num_streams: int = 1, additional_discount: float = 0.99, max_abs_reward: Optional[float] = 1.0,
+               resize_shape: Optional[Tuple[int, int]] = (84, 84), num_action_repeats: int = 4, num_pooled_frames: int = 2,
+               zero_discount_on_life_loss: bool = True, num_stacked_frames: int = 4, grayscaling: bool = True,
+               device: Any = 'cuda', device_observations: bool = False):
+    if not grayscaling or resize_shape is None or num_pooled_frames != 2:
+      raise ValueError('the device preprocessing implements the standard DQN pipeline only: grayscaling=True, '
+                       'a resize_shape, num_pooled_frames=2')
+    if num_action_repeats < 2:
+      raise ValueError('num_action_repeats must be >= num_pooled_frames')
+    self._n = num_streams
+    self._gamma = additional_discount
+    self._clip = max_abs_reward
+    self._out = tuple(resize_shape)
+    self._repeats = num_action_repeats
+    self._life_loss = zero_discount_on_life_loss
+    self._stack = num_stacked_frames
+    self._device = torch.device(device)
+    self._device_obs = device_observations
+    self._streams = [_Stream(num_action_repeats) for _ in range(num_streams)]
+    self._in_shape = None
+    self._luma = (C.c_double * 3)(*LUMA)
+    self._band_rows = int(_lib.lib.dz_atari_preprocess_band_rows())
+
+  # -- device state, created when the first frame tells us the raw geometry ------------------------------------
+  def _allocate(self, shape):
+    h, w, c = shape
+    if c != 3:
+      raise ValueError('expected RGB frames [H, W, 3], got %s' % (shape,))
+    self._in_shape = (h, w, 3)
+    oh, ow = self._out
+    self._axis_h = _Axis(w, ow, self._device)
+    self._axis_v = _Axis(h, oh, self._device)
+    bv = self._axis_v.bounds_host
+    self._max_band_rows = max(
+        int(bv[min(y0 + self._band_rows, oh) - 1].sum() - bv[y0, 0]) for y0 in range(0, oh, self._band_rows))
+    # only the last two slots of the action-repeat buffer are ever pooled (processors.py:485)
+    self._raw = torch.zeros((self._n, 2, h, w, 3), dtype=torch.uint8, device=self._device)
+    self._stacks = torch.zeros((self._n, oh, ow, self._stack), dtype=torch.uint8, device=self._device)
+    self._meta_host = torch.zeros((4, self._n), dtype=torch.int64).pin_memory()
+    self._meta = torch.zeros((4, self._n), dtype=torch.int64, device=self._device)
+    self._counts = torch.zeros(self._n, dtype=torch.int32, device=self._device)
+    self._meta_done = torch.cuda.Event()
+    self._meta_pending = False
+
+  def reset(self, stream: Optional[int] = None) -> None:
+    for i in (range(self._n) if stream is None else [stream]):
+      self._streams[i].reset()
+      if self._in_shape is not None:
+        self._stacks[i].zero_()
+
+  @property
+  def stacks(self) -> torch.Tensor:
+    """uint8 [num_streams, out_h, out_w, num_stacked_frames] on the device (valid after the first emission)."""
+    return self._stacks
+
+  # -- one tick: one raw timestep per stream (None = stream idle this tick) ---------------------------------------
+  def step(self, timesteps: Sequence[Any]) -> List[Any]:
+    if len(timesteps) != self._n:
+      raise ValueError('expected %d timesteps' % self._n)
+    emit = []
+    scalars = [None] * self._n
+    for e, ts in enumerate(timesteps):
+      if ts is None:
+        continue
+      st = self._streams[e]
+      rgb, lives = ts.observation
+      if self._in_shape is None:
+        self._allocate(np.shape(rgb))
+      step_type, reward, discount = ts.step_type, ts.reward, ts.discount
+      if self._life_loss:                       # ZeroDiscountOnLifeLoss, processors.py:254-260
+        lost = step_type == StepType.MID and lives < st.lives
+        st.lives = lives
+        if lost:
+          discount = 0.0
+      if st.index >= self._repeats:             # FixedPaddedBuffer, processors.py:146-154
+        st.index = 0
+        st.slots = [None] * self._repeats
+        st.has_frame = [False] * self._repeats
+      st.slots[st.index] = (step_type, reward, discount)
+      pooled_slot = st.index - (self._repeats - 2)
+      if pooled_slot >= 0:
+        frame = np.ascontiguousarray(rgb, dtype=np.uint8)
+        if frame.shape != self._in_shape:
+          raise ValueError('frame shape changed: %s vs %s' % (frame.shape, self._in_shape))
+        self._raw[e, pooled_slot].copy_(torch.from_numpy(frame), non_blocking=False)
+        st.has_frame[st.index] = True
+      st.index += 1
+      if self._should_emit(st):
+        scalars[e] = self._reduce_scalars(st)
+        emit.append(e)
+    if emit:
+      self._launch(emit)
+    outs = [None] * self._n
+    for e in emit:
+      step_type, reward, discount = scalars[e]
+      obs = self._stacks[e] if self._device_obs else self._stacks[e].cpu().numpy()
+      outs[e] = parts.TimeStep(step_type=step_type, reward=reward, discount=discount, observation=obs)
+    return outs
+
+  def _should_emit(self, st) -> bool:           # TimestepBufferCondition, processors.py:165-215
+    if st.should_reset:
+      raise RuntimeError('Should have reset.')
+    main = StepType.MID
+    for v in st.slots:
+      if v is None:
+        continue
+      if v[0] in (StepType.FIRST, StepType.LAST):
+        if main in (StepType.FIRST, StepType.LAST):
+          raise RuntimeError('Expected at most one FIRST or LAST.')
+        main = v[0]
+    if st.since_first is None and main != StepType.FIRST:
+      raise RuntimeError('After reset first timestep should be FIRST.')
+    if main == StepType.FIRST:
+      st.since_first = 0
+      return True
+    if main == StepType.LAST:
+      st.since_first = None
+      st.should_reset = True
+      return True
+    st.since_first += 1
+    return st.since_first % self._repeats == 0
+
+  def _reduce_scalars(self, st):
+    """none_to_zero_pad + reduce_step_type + aggregate_rewards/discounts (processors.py:54-66, 267-365, 464-481)."""
+    # padding slots: np.zeros_like(None) in the reference is an object-dtype zero, not None — so only a real FIRST
+    # timestep (reward/discount None) makes the aggregate None
+    slots = [(0, 0.0, 0.0) if v is None else v for v in st.slots]
+    out_type = StepType.MID
+    for v in slots:
+      if v[0] == 0:
+        out_type = StepType.FIRST
+        break
+      if v[0] == StepType.LAST:
+        out_type = StepType.LAST
+        break
+      if v[0] != StepType.MID:
+        raise ValueError('Expected MID if not FIRST or LAST.')
+    rewards = [v[1] for v in slots]
+    if any(r is None for r in rewards):
+      reward = None
+    else:
+      reward = sum(rewards)
+      if self._clip:
+        reward = max(min(reward, self._clip), -self._clip)
+    discounts = [v[2] for v in slots]
+    if any(d is None for d in discounts):
+      discount = None
+    else:
+      discount = 1
+      for d in discounts:
+        discount *= d
+      discount = self._gamma * discount
+    return out_type, reward, discount
+
+  def _launch(self, emit):
+    n = len(emit)
+    if self._meta_pending:                      # the previous tick's async H2D copy still owns the pinned buffer
+      self._meta_done.synchronize()
+    meta = self._meta_host
+    for i, e in enumerate(emit):
+      st = self._streams[e]
+      a_ok = st.has_frame[self._repeats - 2] and st.slots[self._repeats - 2] is not None
+      b_ok = st.has_frame[self._repeats - 1] and st.slots[self._repeats - 1] is not None
+      meta[0, i] = self._raw[e, 0].data_ptr() if a_ok else 0
+      meta[1, i] = self._raw[e, 1].data_ptr() if b_ok else 0
+      meta[2, i] = self._stacks[e].data_ptr()
+      meta[3, i] = st.count
+      st.count = min(st.count + 1, self._stack)
+    self._meta.copy_(meta, non_blocking=True)
+    self._meta_done.record()
+    self._meta_pending = True
+    self._counts[:n].copy_(self._meta[3, :n])
+    _lib.call('dz_atari_preprocess', self._meta[0].data_ptr(), self._meta[1].data_ptr(), n, C.byref(self._axis_h.c),
+              C.byref(self._axis_v.c), self._meta[2].data_ptr(), self._counts.data_ptr(), self._stack,
+              C.cast(self._luma, C.c_void_p), self._max_band_rows, torch.cuda.current_stream().cuda_stream)
+
+
+class _SingleStream:
+  """The reference's per-environment processor object: `__call__(timestep)` and `reset()`."""
+
+  def __init__(self, **kwargs):
+    self._batched = BatchedAtariPreprocessor(num_streams=1, **kwargs)
+
+  def reset(self) -> None:
+    self._batched.reset()
+
+  def __call__(self, timestep):
+    return self._batched.step([timestep])[0]
+
+  @property
+  def stack(self) -> torch.Tensor:
+    return self._batched.stacks[0]
+
+
+def atari(additional_discount: float = 0.99, max_abs_reward: Optional[float] = 1.0,
+          resize_shape: Optional[Tuple[int, int]] = (84, 84), num_action_repeats: int = 4, num_pooled_frames: int = 2,
+          zero_discount_on_life_loss: bool = True, num_stacked_frames: int = 4, grayscaling: bool = True,
+          device: Any = 'cuda', device_observations: bool = False):
+  """Standard DQN preprocessing on Atari (processors.py:399-505), pixel path on the GPU.
+
+  Timesteps carry `observation = (rgb uint8 [H, W, 3], lives)` exactly as the reference's environment emits them
+  (the processor selects the RGB entry itself, processors.py:391-393)."""
+  return _SingleStream(additional_discount=additional_discount, max_abs_reward=max_abs_reward, resize_shape=resize_shape,
+                       num_action_repeats=num_action_repeats, num_pooled_frames=num_pooled_frames,
+                       zero_discount_on_life_loss=zero_discount_on_life_loss, num_stacked_frames=num_stacked_frames,
+                       grayscaling=grayscaling, device=device, device_observations=device_observations)

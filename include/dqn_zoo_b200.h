@@ -307,6 +307,27 @@ int dz_test_tc_gemm(const float* d_A, int32_t a_na, int32_t a_nb, int32_t a_ld, 
  * x[row*ld + r]; 0: at x[r*ld + row]) into hi/lo TF32 tile images inside d_work (dz_test_tc_pgemm_work floats),
  * then D[i,j] = sum_r A(i,r) B(j,r).  a_ones_row = a_rows appends a row of ones to A (bias-gradient row), -1: none.
  * splits == 1: + d_bias[j] and ReLU are applied if given; otherwise raw partials at d_C + s*split_stride. */
+/* ---- Atari frame preprocessing ---------------------------------------------------------------
+ * Replaces the observation branch of processors.atari() — np.max over the pooled frame pair, rgb2y, PIL bilinear
+ * resize, frame stack (dqn_zoo/processors.py:367-388, 482-501) — for n_env environment streams per launch.
+ * One resampling axis of Pillow's bilinear filter (libImaging/Resample.c): window [first, first + count) and
+ * fixed-point (22-bit) coefficients per output index; the tables are host-computed by the caller. */
+typedef struct dz_resample_axis {
+  const int32_t* d_bounds;   /* [out_size][2] = (first, count) */
+  const int32_t* d_kk;       /* [out_size][ksize] */
+  int32_t ksize, in_size, out_size;
+} dz_resample_axis;
+/* d_frame_a/b: [n_env] device pointers to uint8 [in_h][in_w][3] raw frames (NULL = zero padding, processors.py:54-66);
+ * d_stacks[e]: device pointer to stream e's uint8 [out_h][out_w][stack]; d_counts[e] = frames already in stream e's stack
+ * (< stack: the new frame goes to channel count; == stack: channels shift left, new frame last);
+ * luma3 = {0.299, 0.587, 1 - (0.299 + 0.587)} (host doubles); max_band_rows = the largest number of input rows any
+ * band of dz_atari_preprocess_band_rows() output rows touches (sizes the shared-memory staging). */
+int dz_atari_preprocess(const uint8_t* const* d_frame_a, const uint8_t* const* d_frame_b, int32_t n_env,
+                        const dz_resample_axis* horizontal, const dz_resample_axis* vertical,
+                        uint8_t* const* d_stacks, const int32_t* d_counts, int32_t stack, const double* luma3,
+                        int32_t max_band_rows, void* stream);
+int32_t dz_atari_preprocess_band_rows(void);
+
 /* Device pointer + element count of an internal learner buffer ("act3", "h1", "dh1", "iqn_hi", "iqn_dhi");
  * tests/tools only. */
 int dz_test_learner_buffer(dz_learner* l, const char* name, float** d_ptr, int64_t* count);

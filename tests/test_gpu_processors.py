@@ -1,0 +1,120 @@
+"""GPU: device Atari preprocessing (dqn_zoo_b200/processors.py + csrc/dz_preprocess.cu) against the reference's golden
+vector (processors_test.py:405-475) and, step by step, against the CPU oracle."""
+
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import processors_oracle as po
+from test_oracle_processors import GOLDEN_INPUT_HASHES, GOLDEN_OUTPUT_HASH, golden_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def ts(step_type, reward, discount, rgb, lives=3):
+  from dqn_zoo_b200 import parts
+  return parts.TimeStep(step_type=parts.StepType(step_type), reward=reward, discount=discount, observation=(rgb, lives))
+
+
+def test_reference_golden_vector_on_device():
+  from dqn_zoo_b200 import processors
+  rgb = golden_inputs()
+  assert [hashlib.sha256(o).hexdigest() for o in rgb] == GOLDEN_INPUT_HASHES
+  processor = processors.atari()
+  steps = [(0, None, None), (1, 0.5, 0.9), (1, 0.2, 0.9), (1, 0, 0.9), (1, 0.1, 0.9)]
+  processed = None
+  for (st, r, d), o in zip(steps, rgb):
+    processed = processor(ts(st, r, d, o))
+  assert processed is not None
+  assert processed.step_type == 1
+  assert processed.reward == pytest.approx(0.5 + 0.2 + 0.0 + 0.1)
+  assert processed.discount == pytest.approx(0.9 ** 4 * 0.99)
+  assert processed.observation.dtype == np.uint8 and processed.observation.shape == (84, 84, 4)
+  assert hashlib.sha256(processed.observation.flatten()).hexdigest() == GOLDEN_OUTPUT_HASH
+
+
+def random_episode(rs, length, shape, life_loss_at=None):
+  frames = [rs.randint(0, 256, size=shape, dtype=np.uint8) for _ in range(length)]
+  out = []
+  for i, f in enumerate(frames):
+    st = 0 if i == 0 else (2 if i == length - 1 else 1)
+    reward = None if st == 0 else float(rs.choice([-3.0, -1.0, 0.0, 0.5, 1.0, 2.0]))
+    discount = None if st == 0 else (0.0 if st == 2 else 1.0)
+    lives = 3 if life_loss_at is None or i < life_loss_at else 2
+    out.append((st, reward, discount, f, lives))
+  return out
+
+
+def same(a, b):
+  if a is None or b is None:
+    return a is None and b is None
+  ok = int(a[0]) == int(b.step_type)
+  ok &= (a[1] is None and b.reward is None) or (a[1] is not None and b.reward is not None and a[1] == b.reward)
+  ok &= (a[2] is None and b.discount is None) or (a[2] is not None and b.discount is not None and a[2] == b.discount)
+  obs = b.observation.cpu().numpy() if torch.is_tensor(b.observation) else b.observation
+  return ok and np.array_equal(a[3], obs)
+
+
+@pytest.mark.parametrize('device_obs', [False, True])
+def test_episodes_match_oracle_step_by_step(device_obs):
+  from dqn_zoo_b200 import processors
+  rs = np.random.RandomState(11)
+  dev = processors.atari(device_observations=device_obs)
+  ref = po.AtariPreprocessor()
+  emitted = 0
+  for length, loss_at in [(1 + 4 * 3, None), (7, 3), (2, None), (18, 9), (5, None)]:
+    dev.reset()
+    ref.reset()
+    for st, r, d, f, lives in random_episode(rs, length, (210, 160, 3), loss_at):
+      want = ref(st, r, d, (f, lives))
+      got = dev(ts(st, r, d, f, lives))
+      assert same(want, got), (length, st)
+      emitted += want is not None
+  assert emitted >= 12
+
+
+def test_other_geometry_and_stack_depth():
+  from dqn_zoo_b200 import processors
+  rs = np.random.RandomState(12)
+  kwargs = dict(resize_shape=(42, 50), num_action_repeats=3, num_stacked_frames=3, max_abs_reward=None, additional_discount=0.9)
+  dev = processors.atari(**kwargs)
+  ref = po.AtariPreprocessor(**kwargs)
+  for length in (10, 4):
+    dev.reset()
+    ref.reset()
+    for st, r, d, f, lives in random_episode(rs, length, (100, 96, 3)):
+      assert same(ref(st, r, d, (f, lives)), dev(ts(st, r, d, f, lives)))
+
+
+def test_many_streams_in_one_launch():
+  from dqn_zoo_b200 import processors
+  rs = np.random.RandomState(13)
+  n = 5
+  dev = processors.BatchedAtariPreprocessor(num_streams=n)
+  refs = [po.AtariPreprocessor() for _ in range(n)]
+  episodes = [random_episode(rs, 9 + 2 * e, (210, 160, 3), life_loss_at=(4 if e % 2 else None)) for e in range(n)]
+  for t in range(max(len(ep) for ep in episodes)):
+    batch, wants = [], []
+    for e in range(n):
+      if t < len(episodes[e]):
+        st, r, d, f, lives = episodes[e][t]
+        batch.append(ts(st, r, d, f, lives))
+        wants.append(refs[e](st, r, d, (f, lives)))
+      else:
+        batch.append(None)
+        wants.append(None)
+    gots = dev.step(batch)
+    for e in range(n):
+      assert same(wants[e], gots[e]), (t, e)
+  assert dev.stacks.shape == (n, 84, 84, 4) and dev.stacks.is_cuda
+
+
+def test_saturated_and_black_frames():
+  from dqn_zoo_b200 import processors
+  for value in (0, 255):
+    dev = processors.atari()
+    ref = po.AtariPreprocessor()
+    f = np.full((210, 160, 3), value, dtype=np.uint8)
+    assert same(ref(0, None, None, (f, 3)), dev(ts(0, None, None, f)))

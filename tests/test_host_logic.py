@@ -161,3 +161,14 @@ def test_two_rank_target_broadcast_and_aggregation_on_gloo(tmp_path):
   for r, (p, o) in enumerate(zip(procs, outs)):
     assert p.returncode == 0, o
     assert 'ok %d' % r in o
+
+
+def test_bilinear_axis_tables_match_oracle():
+  """Host half of the device preprocessing: Pillow's window/coefficient tables (processors.py:381-386 -> PIL)."""
+  from dqn_zoo_b200 import processors
+  from oracle import processors_oracle as po
+  for in_size, out_size in [(160, 84), (210, 84), (100, 42), (96, 50), (84, 84), (50, 84), (7, 5)]:
+    b, k, ks = processors.bilinear_axis(in_size, out_size)
+    ob, ok, oks = po.resample_coeffs(in_size, out_size)
+    assert ks == oks and np.array_equal(b, ob) and np.array_equal(k, ok)
+  assert processors.LUMA == po.LUMA
