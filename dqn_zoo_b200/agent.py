@@ -162,8 +162,11 @@ class _DeviceAgent(parts.Agent):
 
   # -- acting (dqn/agent.py:121-131,169-177) --------------------------------------------------------------
   def _act(self, timestep) -> parts.Action:
-    obs = np.ascontiguousarray(timestep.observation)
-    self._obs_dev.copy_(torch.from_numpy(obs.reshape(-1)))
+    obs = timestep.observation
+    if isinstance(obs, torch.Tensor):        # device-resident frame stack (processors.atari(device_observations=True))
+      self._obs_dev.copy_(obs.reshape(-1))
+    else:
+      self._obs_dev.copy_(torch.from_numpy(np.ascontiguousarray(obs).reshape(-1)))
     L = self._learner
     taus = noise = None
     if self.KIND in ('iqn', 'rainbow'):

@@ -590,9 +590,11 @@ int dz_replay_add(const dz_replay_view* view, const dz_add_record* rec, const ui
   if (rec->slot < 0 || rec->slot >= view->capacity) return fail(DZ_ERANGE, "slot out of range");
   if (rec->n_patches < 0 || rec->n_patches > 4) return fail(DZ_EINVAL, "at most 4 patches");
   uint8_t* row = view->d_obs + rec->slot * 2 * view->obs_stride;
-  if (h_s_tm1) DZ_CUDA_OK(cudaMemcpyAsync(row, h_s_tm1, view->obs_bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  // cudaMemcpyDefault: the sources may be host arrays (the reference's add path) or device buffers (frame stacks kept
+  // in HBM by the device preprocessing) — the driver infers the direction from the unified address space
+  if (h_s_tm1) DZ_CUDA_OK(cudaMemcpyAsync(row, h_s_tm1, view->obs_bytes, cudaMemcpyDefault, (cudaStream_t)stream));
   if (h_s_t)
-    DZ_CUDA_OK(cudaMemcpyAsync(row + view->obs_stride, h_s_t, view->obs_bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    DZ_CUDA_OK(cudaMemcpyAsync(row + view->obs_stride, h_s_t, view->obs_bytes, cudaMemcpyDefault, (cudaStream_t)stream));
   DZ_LAUNCH(apply_add_kernel, 1, 64, 0, stream, *view, *rec);
   return DZ_OK;
 }

@@ -186,7 +186,8 @@ class BatchedAtariPreprocessor:
     outs = [None] * self._n
     for e in emit:
       step_type, reward, discount = scalars[e]
-      obs = self._stacks[e] if self._device_obs else self._stacks[e].cpu().numpy()
+      # a snapshot, not a view: accumulators and the replay keep references across later emissions
+      obs = self._stacks[e].clone() if self._device_obs else self._stacks[e].cpu().numpy()
       outs[e] = parts.TimeStep(step_type=step_type, reward=reward, discount=discount, observation=obs)
     return outs
 

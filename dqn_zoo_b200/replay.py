@@ -279,9 +279,11 @@ def _apply_index_record(view, patches, tree_index=-1, leaf_value=0.0, evict_inde
   rec.tree_index, rec.leaf_value, rec.evict_index, rec.size_after = tree_index, leaf_value, evict_index, size_after
   rec.d_priority = None if d_priority is None else d_priority.data_ptr()
   rec.alpha = alpha
-  _lib.call('dz_replay_add', C.byref(view), C.byref(rec),
-            h_s_tm1.ctypes.data if h_s_tm1 is not None else None,
-            h_s_t.ctypes.data if h_s_t is not None else None, _stream())
+  def addr(x):
+    if x is None:
+      return None
+    return x.data_ptr() if isinstance(x, torch.Tensor) else x.ctypes.data
+  _lib.call('dz_replay_add', C.byref(view), C.byref(rec), addr(h_s_tm1), addr(h_s_t), _stream())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -723,6 +725,16 @@ class _TransitionStore:
 
 
 def _host_obs(x, store):
+  """Flat uint8 view of an observation to be written into a replay row.  Host arrays are copied H2D by
+  dz_replay_add; CUDA tensors (e.g. the frame stack of `processors.atari(device_observations=True)`) are copied
+  device-to-device on the same stream — the device-resident insert path, no host round trip."""
+  if isinstance(x, torch.Tensor) and x.is_cuda:
+    t = x.contiguous()
+    dtype = np.dtype(str(t.dtype).replace('torch.', ''))
+    store.allocate(tuple(t.shape), dtype)
+    if tuple(t.shape) != store.obs_shape or dtype != store.obs_dtype:
+      raise ValueError('observation shape/dtype changed: %s %s' % (tuple(t.shape), dtype))
+    return t.view(torch.uint8).reshape(-1)
   arr = np.ascontiguousarray(x)
   store.allocate(arr.shape, arr.dtype)
   if arr.shape != store.obs_shape or arr.dtype != store.obs_dtype:

@@ -128,6 +128,7 @@ typedef struct dz_add_record {
   double alpha;
 } dz_add_record;
 
+/* s_tm1 / s_t sources may be HOST arrays or DEVICE buffers (cudaMemcpyDefault; NULL = leave the row's bytes). */
 int dz_replay_add(const dz_replay_view* view, const dz_add_record* rec, const uint8_t* h_s_tm1,
                   const uint8_t* h_s_t, void* stream);
 
@@ -317,7 +318,8 @@ typedef struct dz_resample_axis {
   const int32_t* d_kk;       /* [out_size][ksize] */
   int32_t ksize, in_size, out_size;
 } dz_resample_axis;
-/* d_frame_a/b: [n_env] device pointers to uint8 [in_h][in_w][3] raw frames (NULL = zero padding, processors.py:54-66);
+/* d_frame_a/b: [n_env] device pointers to uint8 [in_h][in_w][3] raw frames, 16-byte aligned, 3*in_w % 16 == 0
+ * (NULL = zero padding, processors.py:54-66);
  * d_stacks[e]: device pointer to stream e's uint8 [out_h][out_w][stack]; d_counts[e] = frames already in stream e's stack
  * (< stack: the new frame goes to channel count; == stack: channels shift left, new frame last);
  * luma3 = {0.299, 0.587, 1 - (0.299 + 0.587)} (host doubles); max_band_rows = the largest number of input rows any

@@ -118,3 +118,72 @@ def test_saturated_and_black_frames():
     ref = po.AtariPreprocessor()
     f = np.full((210, 160, 3), value, dtype=np.uint8)
     assert same(ref(0, None, None, (f, 3)), dev(ts(0, None, None, f)))
+
+
+def test_agent_with_device_resident_frames_equals_host_path():
+  """Raw RGB frames -> device preprocessing -> acting -> replay insert, once with host observations (the reference's
+  data flow) and once with the frame stacks staying in HBM (device_observations=True): same actions, same replay."""
+  from dqn_zoo_b200 import agent as ag
+  from dqn_zoo_b200 import learner as dl
+  from dqn_zoo_b200 import processors
+  from dqn_zoo_b200 import replay as dr
+  rs = np.random.RandomState(21)
+  episodes = [random_episode(rs, n, (210, 160, 3), life_loss_at=loss) for n, loss in [(23, 9), (14, None), (31, 17)]]
+
+  def run(device_obs):
+    rep = dr.PrioritizedTransitionReplay(16, dr.Transition(None, None, None, None, None), 0.5, lambda t: 0.5, 1e-3, True,
+                                         np.random.RandomState(3))
+    agent = ag.Rainbow(preprocessor=processors.atari(device_observations=device_obs),
+                       sample_network_input=np.zeros((84, 84, 4), np.uint8), network=dl.NetworkSpec('rainbow', 6),
+                       support=np.linspace(-10, 10, 51), optimizer=None,
+                       transition_accumulator=dr.NStepTransitionAccumulator(3), replay=rep, batch_size=4,
+                       min_replay_capacity_fraction=2.0, learn_period=4, target_network_update_period=16, rng_key=[0, 7],
+                       use_cuda_graph=False)
+    actions = []
+    for ep in episodes:
+      agent.reset()
+      for st, r, d, f, lives in ep:
+        actions.append(agent.step(ts(st, r, d, f, lives)))
+    torch.cuda.synchronize()
+    return actions, rep.get_state()
+
+  a_host, s_host = run(False)
+  a_dev, s_dev = run(True)
+  assert a_host == a_dev
+  assert len(s_host['storage']) == len(s_dev['storage']) > 5
+  for (i0, t0), (i1, t1) in zip(s_host['storage'], s_dev['storage']):
+    assert i0 == i1
+    for x, y in zip(t0, t1):
+      np.testing.assert_array_equal(np.asarray(x), np.asarray(y))
+
+
+def test_luma_of_all_16777216_colours_is_bit_exact():
+  """Every RGB colour once, identity-sized resample (Pillow's weights are then exactly (1, 0)): the kernel's
+  fixed-point screen + float64 fallback must reproduce the oracle's rgb2y (the golden vector's rounding order)."""
+  import ctypes as C
+  from dqn_zoo_b200 import _lib, processors
+  dev = torch.device('cuda')
+  H, W = 65536, 256
+  rows = torch.arange(H, device=dev)
+  frame = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
+  frame[..., 0] = (rows >> 8).to(torch.uint8)[:, None]
+  frame[..., 1] = (rows & 255).to(torch.uint8)[:, None]
+  frame[..., 2] = torch.arange(W, device=dev).to(torch.uint8)[None, :]
+  ax_h, ax_v = processors._Axis(W, W, dev), processors._Axis(H, H, dev)
+  band = int(_lib.lib.dz_atari_preprocess_band_rows())
+  bv = ax_v.bounds_host
+  max_rows = max(int(bv[min(y0 + band, H) - 1].sum() - bv[y0, 0]) for y0 in range(0, H, band))
+  out = torch.zeros((H, W, 1), dtype=torch.uint8, device=dev)
+  a = torch.tensor([frame.data_ptr()], dtype=torch.int64, device=dev)
+  b = torch.zeros(1, dtype=torch.int64, device=dev)
+  s = torch.tensor([out.data_ptr()], dtype=torch.int64, device=dev)
+  counts = torch.zeros(1, dtype=torch.int32, device=dev)
+  luma = (C.c_double * 3)(*processors.LUMA)
+  _lib.call('dz_atari_preprocess', a.data_ptr(), b.data_ptr(), 1, C.byref(ax_h.c), C.byref(ax_v.c), s.data_ptr(),
+            counts.data_ptr(), 1, C.cast(luma, C.c_void_p), max_rows, torch.cuda.current_stream().cuda_stream)
+  torch.cuda.synchronize()
+  got = out[..., 0].cpu().numpy()
+  host = frame.cpu().numpy()
+  for lo in range(0, H, 8192):
+    want = po.rgb2y(host[lo:lo + 8192])
+    assert np.array_equal(got[lo:lo + 8192], want), lo

@@ -31,19 +31,37 @@ def main():
   stream = torch.cuda.current_stream().cuda_stream
 
   def launch():
+    nonlocal stream
     _lib.call('dz_atari_preprocess', a.data_ptr(), b.data_ptr(), n, C.byref(pre._axis_h.c), C.byref(pre._axis_v.c),
               s.data_ptr(), counts.data_ptr(), 4, C.cast(pre._luma, C.c_void_p), pre._max_band_rows, stream)
 
   for _ in range(args.warmup):
     launch()
   torch.cuda.synchronize()
+  # the ctypes call costs more host time than the kernel runs: time a CUDA graph of `inner` launches so that the
+  # device, not the Python launch rate, is what is measured
+  inner = 20
+  side = torch.cuda.Stream()
+  graph = torch.cuda.CUDAGraph()
+  with torch.cuda.stream(side):
+    stream = side.cuda_stream
+    launch()
+    side.synchronize()
+    with torch.cuda.graph(graph, stream=side):
+      stream = torch.cuda.current_stream().cuda_stream
+      for _ in range(inner):
+        launch()
+  stream = torch.cuda.current_stream().cuda_stream
+  outer = max(args.steps // inner, 3)
+  graph.replay()
+  torch.cuda.synchronize()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   e0.record()
-  for _ in range(args.steps):
-    launch()
+  for _ in range(outer):
+    graph.replay()
   e1.record()
   torch.cuda.synchronize()
-  ms = e0.elapsed_time(e1) / args.steps
+  ms = e0.elapsed_time(e1) / (outer * inner)
   alg_bytes = n * (2 * H * W * 3 + 2 * 84 * 84 * 4)
   try:
     peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'MEASURED_PEAKS.json')))
