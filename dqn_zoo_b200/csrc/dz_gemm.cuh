@@ -195,6 +195,7 @@ __device__ __forceinline__ float4 ld4_guard(const float* src, int n, int N, bool
 // ---------------------------------------------------------------------------------------------
 template <int BM, int BN, int BK, int TM, int TN, bool DUAL>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_nn_kernel(const __grid_constant__ GemmBatch batch) {
+  dz::pdl_enter();
   constexpr int NT = (BM / TM) * (BN / TN);
   const GemmProblem& p = batch.p[blockIdx.z];
   const int tiles_m = (p.M + BM - 1) / BM;
@@ -323,6 +324,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) gemm_nn_kernel(const __
 // ---------------------------------------------------------------------------------------------
 template <int BMK, int BN, int BR, int TM, int TN>
 __global__ void __launch_bounds__((BMK / TM) * (BN / TN)) gemm_tn_kernel(const __grid_constant__ GemmBatch batch) {
+  dz::pdl_enter();
   constexpr int NT = (BMK / TM) * (BN / TN);
   const GemmProblem& p = batch.p[blockIdx.z];
   const int Kext = p.K + ((p.Cb || p.Cb2) ? 1 : 0);
@@ -451,6 +453,7 @@ __global__ void __launch_bounds__((BMK / TM) * (BN / TN)) gemm_tn_kernel(const _
 // ---------------------------------------------------------------------------------------------
 template <int BM, int BNK, int BR, int TM, int TN, bool DUAL>
 __global__ void __launch_bounds__((BM / TM) * (BNK / TN)) gemm_nt_kernel(const __grid_constant__ GemmBatch batch) {
+  dz::pdl_enter();
   constexpr int NT = (BM / TM) * (BNK / TN);
   const GemmProblem& p = batch.p[blockIdx.z];
   const int tiles_m = (p.M + BM - 1) / BM;

@@ -149,6 +149,7 @@ struct FinishNN {  // split-K partials of an NN problem -> bias / noisy combine 
 struct FinishNNBatch { FinishNN f[kMaxProblems]; int n; };
 
 __global__ void __launch_bounds__(256) finish_nn_kernel(const __grid_constant__ FinishNNBatch b) {
+  dz::pdl_enter();
   const FinishNN& f = b.f[blockIdx.y];
   long long total = (long long)f.M * f.N;
   if ((f.N & 3) == 0 && ((reinterpret_cast<uintptr_t>(f.partial) | reinterpret_cast<uintptr_t>(f.out) | (uintptr_t)(f.stride * 4)) & 15) == 0) {
@@ -193,6 +194,7 @@ struct FinishTN {  // split partials [Kext][N] of a TN problem -> weight / bias 
 struct FinishTNBatch { FinishTN f[kMaxProblems]; int n; };
 
 __global__ void __launch_bounds__(256) finish_tn_kernel(const __grid_constant__ FinishTNBatch b) {
+  dz::pdl_enter();
   const FinishTN& f = b.f[blockIdx.y];
   int Kext = f.K + ((f.Cb || f.Cb2) ? 1 : 0);
   long long total = (long long)Kext * f.N;
@@ -232,6 +234,7 @@ struct FinishNT {  // split partials [M][K] (+ dual second half) of up to two NT
 };
 
 __global__ void __launch_bounds__(256) finish_nt_kernel(FinishNT f) {
+  dz::pdl_enter();
   long long total = (long long)f.M * f.K;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     float v = 0.f;
@@ -249,6 +252,7 @@ __global__ void __launch_bounds__(256) finish_nt_kernel(FinishNT f) {
 __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ dcol, const float* __restrict__ act,
                                                      float* __restrict__ dx, int nimg, int H, int W, int Cin, int KH, int KW,
                                                      int S, int OH, int OW) {
+  dz::pdl_enter();
   long long total = (long long)nimg * H * W * Cin;
   const int K = KH * KW * Cin;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -279,11 +283,13 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ d
 
 __global__ void add_mask_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ act,
                                 float* __restrict__ out, long long n) {
+  dz::pdl_enter();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < n) out[i] = act[i] > 0.f ? a[i] + b[i] : 0.f;
 }
 
 __global__ void sum_to_scalar_kernel(const float* __restrict__ v, int n, float* out) {
+  dz::pdl_enter();
   __shared__ float s[32];
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) acc += v[i];
@@ -307,6 +313,7 @@ constexpr int kSkinnyMaxN = 18;
 struct SkinnyHead { const float* A[3]; const float* W[3]; const float* bias[3]; float* out[3]; int M[3]; int n; };
 
 __global__ void __launch_bounds__(256) iqn_head_fwd_kernel(const __grid_constant__ SkinnyHead h, int N) {
+  dz::pdl_enter();
   constexpr int K = 512;
   __shared__ __align__(16) float Ws[kSkinnyMaxN * K];
   const int q = blockIdx.y;
@@ -341,6 +348,7 @@ __global__ void __launch_bounds__(256) iqn_head_fwd_kernel(const __grid_constant
 // Input gradient of the same head: dh1[m, k] = [h1 > 0] * sum_a dout[m, a] W[k, a]  (one thread = 4 consecutive k).
 __global__ void __launch_bounds__(256) iqn_head_dgrad_kernel(const float* __restrict__ dout, const float* __restrict__ W,
                                                              const float* __restrict__ h1, float* __restrict__ dh1, int M, int N) {
+  dz::pdl_enter();
   constexpr int K = 512;
   __shared__ float Ws[K * kSkinnyMaxN];
   for (int i = threadIdx.x; i < K * N; i += 256) Ws[i] = W[i];
@@ -365,6 +373,7 @@ __global__ void __launch_bounds__(256) iqn_head_dgrad_kernel(const float* __rest
 
 // cos(pi * i * tau), i = 1..latent; the product is formed in float32 as in networks.py:277-278.
 __global__ void iqn_cos_kernel(const float* __restrict__ taus, float* __restrict__ out, long long rows, int latent) {
+  dz::pdl_enter();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= rows * latent) return;
   int j = (int)(i % latent);
@@ -376,6 +385,7 @@ __global__ void iqn_cos_kernel(const float* __restrict__ taus, float* __restrict
 __global__ void __launch_bounds__(256) iqn_hadamard_bwd_kernel(float* __restrict__ dHI, const float* __restrict__ E,
                                                                const float* __restrict__ F, float* __restrict__ dfeat,
                                                                int B, int N, int D) {
+  dz::pdl_enter();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)B * D) return;
   int b = (int)(i / D), k = (int)(i % D);
@@ -396,6 +406,7 @@ __global__ void __launch_bounds__(256) iqn_hadamard_bwd_packed_kernel(const floa
                                                                       const float* __restrict__ F, float* __restrict__ dfeat,
                                                                       float* __restrict__ img_hi, float* __restrict__ img_lo,
                                                                       int rg_total, int D) {
+  dz::pdl_enter();
   constexpr int N = 64;
   __shared__ float tile[64][65];
   __shared__ float red[16][64];
@@ -459,6 +470,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 // kind 0: U[0,1) (IQN taus); kind 1: sign(n)*sqrt|n|, n ~ TruncNormal(-2,2) (networks.py:142-144).
 __global__ void randomness_kernel(float* __restrict__ out, long long n, uint64_t seed, const int64_t* counters, int kind,
                                   uint32_t stream_id) {
+  dz::pdl_enter();
   long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i4 * 4 >= n) return;
   uint64_t ctr = (uint64_t)counters[1];
@@ -482,7 +494,8 @@ __global__ void randomness_kernel(float* __restrict__ out, long long n, uint64_t
   }
 }
 
-__global__ void bump_counter_kernel(int64_t* counters, int which) { counters[which] += 1; }
+__global__ void bump_counter_kernel(int64_t* counters, int which) {
+  dz::pdl_enter(); counters[which] += 1; }
 
 // ---- losses ------------------------------------------------------------------------------------
 
@@ -525,6 +538,7 @@ __device__ __forceinline__ float block_max(float v, float* smem) {
 
 // dqn / double_q / prioritized: rlax.q_learning / double_q_learning, clip_gradient, l2_loss.
 __global__ void __launch_bounds__(64) loss_q_kernel(LossArgs L) {
+  dz::pdl_enter();
   int b = blockIdx.x;
   if (threadIdx.x != 0) return;
   const float* q_tm1 = L.out0 + (long long)b * L.A;
@@ -550,6 +564,7 @@ __global__ void __launch_bounds__(64) loss_q_kernel(LossArgs L) {
 __device__ __forceinline__ float warp_sum_all(float v) { return warp_sum(v); }
 
 __global__ void __launch_bounds__(128) loss_categorical_kernel(LossArgs L) {
+  dz::pdl_enter();
   extern __shared__ float sm[];
   const int b = blockIdx.x, K = L.atoms, A = L.A, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float* cm_sel = sm;            // [K] mean over actions of the selector-pass advantages (rainbow)
@@ -679,6 +694,7 @@ __global__ void __launch_bounds__(128) loss_categorical_kernel(LossArgs L) {
 // qrdqn / iqn: rlax.quantile_q_learning with quantile_regression_loss (Huber kappa).
 // Layouts: qrdqn out[b, q*A + a] (networks.py:308), iqn out[(b*N + n)*A + a] (networks.py:286-287).
 __global__ void __launch_bounds__(256) loss_quantile_kernel(LossArgs L) {
+  dz::pdl_enter();
   extern __shared__ float sm[];
   const int b = blockIdx.x, A = L.A, tid = threadIdx.x;
   const bool iqn = L.kind == DZ_IQN;
@@ -745,6 +761,7 @@ __global__ void __launch_bounds__(256) loss_quantile_kernel(LossArgs L) {
 }
 
 __global__ void loss_mean_kernel(const float* __restrict__ terms, int B, float* loss, float* max_seen, const float* priorities) {
+  dz::pdl_enter();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     float s = 0.f;
     for (int b = 0; b < B; ++b) s += terms[b];
@@ -760,6 +777,7 @@ __global__ void loss_mean_kernel(const float* __restrict__ terms, int B, float* 
 // q_values of one head pass (select_action): c51/rainbow expectation, qr/iqn mean, dqn identity.
 __global__ void __launch_bounds__(128) q_values_kernel(int kind, int A, int atoms, int nq, float vmax, const float* out,
                                                        const float* adv, const float* val, float* q) {
+  dz::pdl_enter();
   extern __shared__ float sm[];
   float* red = sm;
   float* logit = sm + 32;
@@ -808,6 +826,7 @@ __global__ void __launch_bounds__(128) q_values_kernel(int kind, int A, int atom
 // (deterministic), publishes the global norm and bumps the optimizer step count.
 __global__ void __launch_bounds__(256) grad_norm_kernel(const float* __restrict__ g, long long n, float* partials,
                                                         unsigned int* ticket, float* norm_out, int64_t* counters, float* user_norm) {
+  dz::pdl_enter();
   __shared__ float s[32];
   __shared__ bool last;
   float acc = 0.f;
@@ -880,6 +899,7 @@ __device__ __forceinline__ float opt_one(const OptArgs& o, float p, float g, flo
 // SLOWER — 124 vs 80 us for rainbow: most of the 137 MB of state survives in the 126 MB L2 between steps.)
 template <int KIND>
 __global__ void __launch_bounds__(256) optimizer_kernel(OptArgs o) {
+  dz::pdl_enter();
   const float norm = o.norm[0];
   const bool clip = o.max_norm > 0.f && !(norm < o.max_norm);  // optax.clip_by_global_norm trigger
   float c1 = 1.f, c2 = 1.f;
@@ -917,6 +937,7 @@ __global__ void __launch_bounds__(256) optimizer_kernel(OptArgs o) {
 }
 
 __global__ void make_row_table_kernel(const uint8_t* base, long long stride, int n, const uint8_t** table) {
+  dz::pdl_enter();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) table[i] = base + (long long)i * stride;
 }
@@ -974,6 +995,7 @@ constexpr int kNormBlocks = 592;
 // The packed-operand tcgen05 kernels carry IQN's 3136->512 layer whenever every network apply has >= 1024 rows
 // (DZ_PK_IQN=0 falls back to the fp32-FMA kernels, for A/B timing).
 bool g_pk_iqn = true;
+int g_fc_splits = 0;      // DZ_FC_SPLITS override
 void read_env();
 
 // Split count for a one-CTA-per-SM kernel: minimise (waves of 148 CTAs) x (k-blocks per split).
@@ -1009,7 +1031,7 @@ int64_t carve(dz_learner* l, char* base) {
     l->hi[p] = iqn ? w.take<float>(rows * d.feat) : nullptr;
   }
   l->E0 = iqn ? w.take<float>((int64_t)B * nh[0] * d.feat) : nullptr;
-  l->fc_splits = 14; l->head_splits = 8; l->conv_splits = 4; l->nt_splits = 8;
+  l->fc_splits = g_fc_splits > 0 ? std::min(g_fc_splits, 64) : 14; l->head_splits = 8; l->conv_splits = 4; l->nt_splits = 8;
   {
     int64_t head_n = std::max<int64_t>(d.out, c.num_atoms);
     int64_t fc = (int64_t)kMaxProblems * l->fc_splits * 2 * B * 512;
@@ -1137,6 +1159,7 @@ void read_env() {
   g_use_tc = getenv("DZ_TC") != nullptr && std::string(getenv("DZ_TC")) != "0";
   g_tc_layers = getenv("DZ_TC") ? getenv("DZ_TC") : "";
   g_pk_iqn = !(getenv("DZ_PK_IQN") != nullptr && std::string(getenv("DZ_PK_IQN")) == "0");
+  g_fc_splits = getenv("DZ_FC_SPLITS") ? atoi(getenv("DZ_FC_SPLITS")) : 0;
 }
 
 bool tc_enabled_for(const char* tag) {

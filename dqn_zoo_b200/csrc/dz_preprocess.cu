@@ -64,6 +64,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
 __device__ __forceinline__ uint8_t clip8(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
 
 __global__ void __launch_bounds__(256) atari_preprocess_kernel(const PreprocessArgs a) {
+  dz::pdl_enter();
   extern __shared__ __align__(16) uint8_t smem[];
   const int env = blockIdx.y;
   const int kBandRows = a.band;

@@ -12,6 +12,7 @@ namespace dz {
 
 thread_local std::string g_last_error;
 std::atomic<int64_t> g_launches{0};
+int g_pdl = -1;
 bool g_profile = false;
 
 namespace {
@@ -69,6 +70,7 @@ constexpr int kSetChunk = 1024;
 __global__ void __launch_bounds__(256) sumtree_set_kernel(double* nodes, int64_t first_leaf, int64_t size,
                                                           const int64_t* __restrict__ idx,
                                                           const double* __restrict__ vals, int n, int32_t* flags) {
+  dz::pdl_enter();
   __shared__ int64_t s_idx[kSetChunk];
   __shared__ double s_val[kSetChunk];
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -99,6 +101,7 @@ __global__ void __launch_bounds__(256) update_priorities_kernel(double* nodes, i
                                                                 const int64_t* __restrict__ idx,
                                                                 const float* __restrict__ pri, int n, double alpha,
                                                                 int32_t* flags) {
+  dz::pdl_enter();
   __shared__ int64_t s_idx[kSetChunk];
   __shared__ double s_val[kSetChunk];
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -125,6 +128,7 @@ __global__ void __launch_bounds__(32) update_priorities_warp_kernel(double* node
                                                                     const int64_t* __restrict__ idx,
                                                                     const float* __restrict__ pri, int n, double alpha,
                                                                     int32_t* flags) {
+  dz::pdl_enter();
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x;
   int64_t k = -1;
@@ -177,11 +181,13 @@ __global__ void __launch_bounds__(32) update_priorities_warp_kernel(double* node
 // Level-by-level rebuild (replay.py:394-404).  One launch per level keeps it simple and is only
 // used by set_all / resize / set_state (never on the hot path).
 __global__ void sumtree_zero_tail_kernel(double* nodes, int64_t first_leaf, int64_t n_valid) {
+  dz::pdl_enter();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x + n_valid;
   if (i < first_leaf) nodes[first_leaf + i] = 0.0;
   if (blockIdx.x == 0 && threadIdx.x == 0) nodes[0] = 0.0;
 }
 __global__ void sumtree_level_kernel(double* nodes, int64_t width) {
+  dz::pdl_enter();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < width) {
     int64_t p = width + i;
@@ -190,6 +196,7 @@ __global__ void sumtree_level_kernel(double* nodes, int64_t width) {
 }
 // Top of the tree (<= 2048 leaves under it) in one block.
 __global__ void __launch_bounds__(1024) sumtree_top_kernel(double* nodes, int64_t width_start) {
+  dz::pdl_enter();
   for (int64_t width = width_start; width >= 1; width >>= 1) {
     for (int64_t i = threadIdx.x; i < width; i += blockDim.x) {
       int64_t p = width + i;
@@ -235,6 +242,7 @@ __device__ int64_t warp_tree_descend(const double* __restrict__ nodes, int depth
 __global__ void __launch_bounds__(256) sumtree_query_kernel(const double* __restrict__ nodes, int64_t first_leaf,
                                                             const double* __restrict__ targets, int64_t n,
                                                             int64_t* __restrict__ out, int32_t* flags) {
+  dz::pdl_enter();
   int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (q >= n) return;
   double root = nodes[1];
@@ -253,6 +261,7 @@ __global__ void __launch_bounds__(256) sumtree_query_kernel(const double* __rest
 __global__ void sumtree_get_kernel(const double* __restrict__ nodes, int64_t first_leaf, int64_t size,
                                    const int64_t* __restrict__ idx, int64_t n, double* __restrict__ out,
                                    int32_t* flags) {
+  dz::pdl_enter();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   int64_t k = idx[i];
@@ -288,6 +297,7 @@ __device__ void emit_batch_rows(const dz_replay_view& v, const BatchExtras& ex, 
 
 __global__ void __launch_bounds__(1024) per_sample_kernel(dz_replay_view v, dz_sample_inputs in, dz_sample_outputs out,
                                                           int batch, BatchExtras ex) {
+  dz::pdl_enter();
   extern __shared__ double s_w[];  // [batch] unnormalised weights
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const double* nodes = v.d_tree;
@@ -352,6 +362,7 @@ __global__ void __launch_bounds__(1024) per_sample_kernel(dz_replay_view v, dz_s
 
 __global__ void uniform_sample_kernel(dz_replay_view v, dz_sample_inputs in, dz_sample_outputs out, int batch,
                                       BatchExtras ex) {
+  dz::pdl_enter();
   int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= batch) return;
   int64_t pos = in.d_rand_pos[q];
@@ -372,6 +383,7 @@ __global__ void uniform_sample_kernel(dz_replay_view v, dz_sample_inputs in, dz_
 __global__ void __launch_bounds__(256) gather_obs_kernel(dz_replay_view v, const int64_t* __restrict__ slots,
                                                          uint8_t* __restrict__ s_tm1, uint8_t* __restrict__ s_t,
                                                          int vec16) {
+  dz::pdl_enter();
   const int b = blockIdx.y >> 1, which = blockIdx.y & 1;
   const uint8_t* src = v.d_obs + (slots[b] * 2 + which) * v.obs_stride;
   uint8_t* dst = (which ? s_t : s_tm1) + (int64_t)b * v.obs_bytes;
@@ -390,6 +402,7 @@ __global__ void __launch_bounds__(256) gather_obs_kernel(dz_replay_view v, const
 
 __global__ void gather_scalars_kernel(dz_replay_view v, const int64_t* __restrict__ slots, int batch, int64_t* a,
                                       double* r, double* d) {
+  dz::pdl_enter();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
   int64_t s = slots[b];
@@ -403,6 +416,7 @@ __global__ void gather_scalars_kernel(dz_replay_view v, const int64_t* __restric
 // ------------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(64) apply_add_kernel(dz_replay_view v, dz_add_record rec) {
+  dz::pdl_enter();
   __shared__ int64_t s_idx[2];
   __shared__ double s_val[2];
   if (threadIdx.x == 0) {
@@ -439,6 +453,7 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 }
 
 __global__ void __launch_bounds__(256) fill_obs_kernel(dz_replay_view v, int64_t row0, int64_t n, uint64_t seed) {
+  dz::pdl_enter();
   const int64_t words = v.obs_bytes >> 3;
   const int64_t total = n * 2 * words;
   const uint64_t base = seed * 0x9E3779B97F4A7C15ull;
@@ -455,6 +470,7 @@ __global__ void __launch_bounds__(256) fill_obs_kernel(dz_replay_view v, int64_t
 
 __global__ void fill_scalars_kernel(dz_replay_view v, int64_t row0, int64_t n, uint64_t seed, int num_actions,
                                     double discount) {
+  dz::pdl_enter();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   int64_t row = row0 + i;

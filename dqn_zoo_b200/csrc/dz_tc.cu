@@ -61,7 +61,8 @@ int launch_tc(const char* tag, const TcBatch& tb_in, int bnj, void* stream) {
 using namespace dz;
 
 namespace {
-__global__ void u8_to_unit_table_kernel(float* out) { out[threadIdx.x] = u8_to_unit(threadIdx.x); }
+__global__ void u8_to_unit_table_kernel(float* out) {
+  dz::pdl_enter(); out[threadIdx.x] = u8_to_unit(threadIdx.x); }
 }  // namespace
 
 extern "C" int dz_test_u8_to_unit(float* d_out256, void* stream) {

@@ -358,6 +358,7 @@ struct SmemLayout {
 // A_KSRC / B_KSRC: the operand's source is contiguous along the reduction index (uniform over the batch).
 template <int BNJ, int STAGES, bool A_KSRC, bool B_KSRC, bool A_EXACT>
 __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_constant__ TcBatch batch) {
+  dz::pdl_enter();
   extern __shared__ __align__(128) uint8_t smem[];
   using L = SmemLayout<BNJ, STAGES>;
   const TcProblem& p = batch.p[blockIdx.z];

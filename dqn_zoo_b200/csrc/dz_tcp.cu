@@ -20,6 +20,7 @@ int pk_add_job(PackBatch& pb, const float* src, int ld, int red_contig, int rows
 
 namespace {
 __global__ void pk_ones_row_kernel(float* hi, int rg_total, int row, int red) {
+  dz::pdl_enter();
   int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m < red) hi[(((((long long)(m >> 4) * rg_total + (row >> 3)) << 2) + ((m & 15) >> 2)) << 5) + (row & 7) * 4 + (m & 3)] = 1.f;
 }

@@ -45,6 +45,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
 // One block = one 64-row x 64-deep tile, staged through shared memory so that both the source reads (either
 // orientation) and the image writes (512-byte runs) are coalesced.
 __global__ void __launch_bounds__(256) tc_pack_kernel(const __grid_constant__ PackBatch pb) {
+  dz::pdl_enter();
   __shared__ float tile[64][65];
   int j = 0;
   while (j + 1 < pb.n && (int)blockIdx.x >= pb.job[j + 1].block0) ++j;
@@ -132,6 +133,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 //        hi/lo tile images of the NEXT GEMMs' operands (rows i, and optionally the transposed rows j).
 template <int BNJ, int EPI>
 __global__ void __launch_bounds__(kThreadsP, EPI ? 2 : 1) tc_pgemm_kernel(const __grid_constant__ PkBatch batch) {
+  dz::pdl_enter();
   extern __shared__ __align__(128) uint8_t smem[];
   using L = PkSmem<BNJ, EPI>;
   constexpr int ST = L::kStages;
