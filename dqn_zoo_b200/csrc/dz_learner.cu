@@ -895,8 +895,10 @@ __device__ __forceinline__ float opt_one(const OptArgs& o, float p, float g, flo
 }
 
 // 7 floats of traffic per parameter (read p,g,m,v; write p,m,v), 16-byte accesses, 4 independent
-// float4 quadruples per thread in flight.  (Streaming / evict-first hints on g, m, v were measured
-// SLOWER — 124 vs 80 us for rainbow: most of the 137 MB of state survives in the 126 MB L2 between steps.)
+// float4 quadruples per thread in flight.  Measured alternatives (rainbow, 52.7 us per launch incl. ~5 us of
+// event overhead): ld.global.cs on the gradient and/or st.global.cs on the moments: no change (52.7 / 53.0 us);
+// 4 quadruples per thread: 71 us (register pressure halves the resident threads); 4, 8, 12, 16 blocks per SM:
+// 43.9 / 45.0 / 45.8 / 46.7 us.
 template <int KIND>
 __global__ void __launch_bounds__(256) optimizer_kernel(OptArgs o) {
   dz::pdl_enter();
