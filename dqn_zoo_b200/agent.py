@@ -390,5 +390,100 @@ def _check_support(support, network):
     raise ValueError('support must be linspace(-vmax, vmax, num_atoms) of the NetworkSpec')
 
 
+class EpsilonGreedyActor(parts.Agent):
+  """Acts epsilon-greedily with externally supplied network parameters (parts.py:336-411): the evaluation agent of
+  the run drivers (`eval_agent.network_params = train_agent.online_params`, dqn/run_atari.py:260).
+
+  `network_params` accepts what `agent.online_params` returns (haiku-shaped nested dict of host arrays), a flat
+  `{canonical_name: array}` dict, or — the device-resident shortcut — the training learner itself
+  (`eval_agent.network_params = train_agent.learner`: one D2D copy of the parameter blob).  The epsilon draw uses a
+  host RandomState seeded from `rng_key` (the reference uses the JAX PRNG; action-sequence parity with it is SURVEY
+  §8(f) #2)."""
+
+  def __init__(self, preprocessor, network: NetworkSpec, exploration_epsilon: float, rng_key, device=None):
+    self._preprocessor = preprocessor
+    self._net = network
+    self._epsilon = float(exploration_epsilon)
+    self._learner = learner_lib.Learner(network, batch_size=1, device=device)
+    self._rng = np.random.RandomState(int(np.asarray(rng_key).reshape(-1)[-1]) & 0x7FFFFFFF)
+    self._seed = int(np.asarray(rng_key).reshape(-1)[-1]) & 0x7FFFFFFF
+    self._obs_dev = torch.zeros(int(np.prod(network.obs_shape)), dtype=torch.uint8, device=self._learner.device)
+    self._action = None
+    self._has_params = False
+
+  @property
+  def network_params(self):
+    return self._learner.haiku_params('online') if self._has_params else None
+
+  @network_params.setter
+  def network_params(self, params) -> None:
+    if params is None:
+      self._has_params = False
+      return
+    if isinstance(params, learner_lib.Learner):
+      self._learner.online.copy_(params.online)
+    else:
+      flat = {}
+      for key, value in params.items():
+        if isinstance(value, Mapping):            # haiku-shaped {module: {leaf: array}}
+          for leaf, arr in value.items():
+            flat[self._canonical(key, leaf)] = arr
+        else:
+          flat[key] = value
+      self._learner.set_params(flat)
+    self._has_params = True
+
+  def _canonical(self, module, leaf):
+    for name in self._learner.tensors:
+      if learner_lib.haiku_name(name, self._learner.kind) == (module, leaf):
+        return name
+    raise KeyError('unknown parameter %s/%s' % (module, leaf))
+
+  def step(self, timestep) -> parts.Action:
+    timestep = self._preprocessor(timestep)
+    if timestep is None:
+      if self._action is None:
+        raise RuntimeError('Cannot repeat if action has never been selected.')
+      return self._action
+    if not self._has_params:
+      raise RuntimeError('network_params have not been set.')
+    obs = timestep.observation
+    if isinstance(obs, torch.Tensor):
+      self._obs_dev.copy_(obs.reshape(-1))
+    else:
+      self._obs_dev.copy_(torch.from_numpy(np.ascontiguousarray(obs).reshape(-1)))
+    L = self._learner
+    taus = noise = None
+    if L.kind in ('iqn', 'rainbow'):
+      self._seed += 1
+      L.generate_randomness(self._seed)
+      taus = L.taus if L.kind == 'iqn' else None
+      noise = L.noise if L.kind == 'rainbow' else None
+    q = L.q_values(self._obs_dev, taus=taus, noise=noise).cpu().numpy()
+    if self._epsilon > 0.0 and self._rng.uniform() < self._epsilon:
+      self._action = parts.Action(int(self._rng.randint(len(q))))
+    else:
+      self._action = parts.Action(int(np.argmax(q)))
+    return self._action
+
+  def reset(self) -> None:
+    if hasattr(self._preprocessor, 'reset'):
+      self._preprocessor.reset()
+    self._action = None
+
+  def get_state(self) -> Mapping[str, Any]:
+    return {'rng_key': (self._rng.get_state(), self._seed),
+            'network_params': self._learner.get_params('online') if self._has_params else None}
+
+  def set_state(self, state: Mapping[str, Any]) -> None:
+    rng_state, self._seed = state['rng_key']
+    self._rng.set_state(rng_state)
+    self.network_params = state['network_params']
+
+  @property
+  def statistics(self) -> Mapping[str, float]:
+    return {}
+
+
 AGENTS = {'dqn': Dqn, 'double_q': DoubleQ, 'prioritized': PrioritizedDqn, 'c51': C51, 'qrdqn': QrDqn,
           'rainbow': Rainbow, 'iqn': Iqn}

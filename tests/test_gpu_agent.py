@@ -211,3 +211,74 @@ def test_agent_runs_in_run_loop_and_state_round_trips(kind):
   ids_a = [i for i, _ in a._replay.get_state()['storage']]
   ids_b = [i for i, _ in b._replay.get_state()['storage']]
   assert ids_a == ids_b
+
+
+@pytest.mark.parametrize('kind', ['dqn', 'rainbow'])
+def test_train_eval_iteration_with_trackers_actor_and_checkpoint(kind, tmp_path):
+  """The structure of dqn/run_atari.py:237-290 on a dummy environment: train phase -> eval actor takes the online
+  parameters -> statistics -> CSV row -> checkpoint; then a second process restores and continues identically."""
+  import collections
+  import itertools
+  from dqn_zoo_b200 import agent as ag
+  from dqn_zoo_b200 import learner as dl
+  from dqn_zoo_b200 import parts
+  from dqn_zoo_b200 import replay as dr
+  from dqn_zoo_b200 import reporting
+  structure = dr.Transition(None, None, None, None, None)
+
+  def build(path):
+    rs = np.random.RandomState(2)
+    if kind == 'rainbow':
+      rep = dr.PrioritizedTransitionReplay(64, structure, 0.5, lambda t: 0.5, 1e-3, True, rs)
+    else:
+      rep = dr.TransitionReplay(64, structure, rs)
+    train = _make_agent(kind, rep, 13, False, preprocessor=_RepeatEvery2(), min_replay_capacity_fraction=0.25)
+    evaluator = ag.EpsilonGreedyActor(preprocessor=_RepeatEvery2(), network=dl.NetworkSpec(kind, 6),
+                                      exploration_epsilon=0.05, rng_key=[0, 99])
+    ck = reporting.FileCheckpoint(path)
+    ck.state.iteration = 0
+    ck.state.train_agent = train
+    ck.state.eval_agent = evaluator
+    ck.state.random_state = rs
+    ck.state.writer = reporting.CsvWriter(str(tmp_path / ('results_%s.csv' % kind)))
+    return ck
+
+  def iteration(ck, seed):
+    st = ck.state
+    train_seq = itertools.islice(parts.run_loop(st.train_agent, _Env(seed), max_steps_per_episode=30), 120)
+    train_stats = reporting.generate_statistics(reporting.make_default_trackers(st.train_agent), train_seq)
+    st.eval_agent.network_params = st.train_agent.online_params if seed % 2 else st.train_agent.learner
+    eval_seq = itertools.islice(parts.run_loop(st.eval_agent, _Env(seed + 100), max_steps_per_episode=30), 60)
+    eval_stats = reporting.generate_statistics(reporting.make_default_trackers(st.eval_agent), eval_seq)
+    st.writer.write(collections.OrderedDict([('iteration', st.iteration), ('train_episode_return', train_stats['episode_return']),
+                                             ('eval_episode_return', eval_stats['episode_return']),
+                                             ('train_num_episodes', train_stats['num_episodes']),
+                                             ('train_state_value', train_stats['state_value'])]))
+    st.iteration += 1
+    return train_stats, eval_stats
+
+  path = str(tmp_path / ('ck_%s.pkl' % kind))
+  ck = build(path)
+  t0, e0 = iteration(ck, 1)
+  assert t0['num_steps'] == 120 and e0['num_steps'] == 60 and np.isfinite(t0['state_value'])
+  got = ck.state.eval_agent.network_params
+  want = ck.state.train_agent.online_params
+  for mod in want:
+    for leaf in want[mod]:
+      np.testing.assert_array_equal(got[mod][leaf], want[mod][leaf])
+  ck.save()
+  t1, e1 = iteration(ck, 2)                 # continue in the same "process"
+  ck2 = build(path)                         # a fresh one restores and must reproduce that iteration
+  assert ck2.can_be_restored()
+  ck2.restore()
+  assert ck2.state.iteration == 1
+  t1b, e1b = iteration(ck2, 2)
+  for key in ('episode_return', 'num_episodes', 'num_steps_over_episodes', 'state_value'):
+    assert t1[key] == t1b[key] or (np.isnan(t1[key]) and np.isnan(t1b[key])), key
+  assert e1['episode_return'] == e1b['episode_return'] or (np.isnan(e1['episode_return']) and np.isnan(e1b['episode_return']))
+  a = ck.state.train_agent.get_state()
+  b = ck2.state.train_agent.get_state()
+  for name in a['online_params']:
+    np.testing.assert_array_equal(a['online_params'][name], b['online_params'][name])
+  rows = open(str(tmp_path / ('results_%s.csv' % kind))).read().strip().splitlines()
+  assert rows[0].startswith('iteration,train_episode_return') and len(rows) == 4   # header + it0 + it1 + it1 again
