@@ -134,7 +134,7 @@ def reference_arm(args, rank, world):
       'e2e': {'value': value, 'unit': 'grad-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
       'gpu_launches': 0,
   }
-  print(json.dumps(line), flush=True)
+  emit(line)
 
 
 def build_agent(args, rank, device):
@@ -175,8 +175,28 @@ def build_agent(args, rank, device):
   return ag, rep
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+  """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on rank 0),
+  so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor."""
+  global _REAL_STDOUT
+  if _REAL_STDOUT is None:
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+
+
+def emit(line):
+  out = _REAL_STDOUT or sys.stdout
+  out.write(json.dumps(line) + '\n')
+  out.flush()
+
+
 def main():
   args = parse()
+  guard_stdout()
   rank = int(os.environ.get('RANK', '0'))
   local_rank = int(os.environ.get('LOCAL_RANK', '0'))
   world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -376,7 +396,7 @@ def main():
         'learner_tflops_achieved': GFLOP_PER_STEP[args.agent] * value / world / 1e3,
         'cpu_baseline': cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
   if dist is not None:
     dist.destroy_process_group()
 
