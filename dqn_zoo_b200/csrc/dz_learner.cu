@@ -963,6 +963,8 @@ struct dz_learner {
   float *cosf[3], *hi[3], *E0;             // iqn
   float* nn_partial;                        // split-K partials for the M=batch FC layers and heads
   float* conv_partial;                      // split-K partials for conv2/conv3 forward
+  float* conv1_partial;                     // split-K partials for conv1 forward (conv1_splits > 1)
+  int conv1_splits;
   float* nt_partial;                        // split partials of the input-gradient (NT) GEMMs
   float *dout, *doutv, *dh1[2], *dact3, *dtmp[2], *dcol, *dact2, *dact1, *dhi;
   float* tn_partial[4];                     // conv1/2/3 wgrad partials, [3] = iqn head/embed partial
@@ -998,6 +1000,9 @@ constexpr int kNormBlocks = 592;
 // (DZ_PK_IQN=0 falls back to the fp32-FMA kernels, for A/B timing).
 bool g_pk_iqn = true;
 int g_fc_splits = 0;      // DZ_FC_SPLITS override
+int g_conv1_splits = 1;   // DZ_CONV1_SPLITS: split-K of the conv1 forward GEMM (K = 256).  Measured: rainbow (3 applies,
+                          // 600 tiles) 336 / 344 / 341 us per step for 1 / 2 / 3 splits, dqn (2 applies) 217 / 213 / 217 us:
+                          // the extra finish launch eats the gain, so the default stays 1.
 void read_env();
 
 // Split count for a one-CTA-per-SM kernel: minimise (waves of 148 CTAs) x (k-blocks per split).
@@ -1040,6 +1045,8 @@ int64_t carve(dz_learner* l, char* base) {
     int64_t hd = (int64_t)kMaxProblems * l->head_splits * 2 * B * head_n;
     l->nn_partial = w.take<float>(std::max(fc, hd));
     l->conv_partial = w.take<float>((int64_t)3 * l->conv_splits * B * d.h2 * d.w2 * 64);
+    l->conv1_splits = std::max(1, std::min(g_conv1_splits, 4));
+    l->conv1_partial = l->conv1_splits > 1 ? w.take<float>((int64_t)3 * l->conv1_splits * B * d.h1 * d.w1 * 32) : nullptr;
     l->nt_partial = w.take<float>((int64_t)2 * l->nt_splits * 2 * B * std::max<int64_t>(d.feat, 512));
   }
   int64_t rows0 = (int64_t)B * nh[0];
@@ -1162,6 +1169,7 @@ void read_env() {
   g_tc_layers = getenv("DZ_TC") ? getenv("DZ_TC") : "";
   g_pk_iqn = !(getenv("DZ_PK_IQN") != nullptr && std::string(getenv("DZ_PK_IQN")) == "0");
   g_fc_splits = getenv("DZ_FC_SPLITS") ? atoi(getenv("DZ_FC_SPLITS")) : 0;
+  g_conv1_splits = getenv("DZ_CONV1_SPLITS") ? atoi(getenv("DZ_CONV1_SPLITS")) : 1;
 }
 
 bool tc_enabled_for(const char* tag) {
@@ -1415,14 +1423,21 @@ int forward_torso(dz_learner* l, const TorsoJob* jobs, int njobs, int nimg, void
   const Layout& L = l->lay;
   GemmBatch gb;
   gb.n = njobs;
+  float* outs1[kMaxProblems];
   for (int i = 0; i < njobs; ++i) {   // conv1: uint8 rows gathered in place (K1 + K2 of SURVEY §2.1)
     GemmProblem p = zero_problem();
     set_conv(p, A_CONV_U8, jobs[i].rows, nimg, d.H, d.W, d.C, 8, 8, 4);
     p.B = jobs[i].params + L.off("conv1/w"); p.bias = jobs[i].params + L.off("conv1/b");
     p.N = 32; p.ldb = 32; p.ldc = 32; p.relu = 1; p.C = l->act1[jobs[i].set];
+    outs1[i] = p.C;
+    if (l->conv1_splits > 1 && nimg == l->B) {
+      p.splits = l->conv1_splits; p.split_stride = (long long)p.M * 32;
+      p.C = l->conv1_partial + (long long)i * p.splits * p.split_stride;
+    }
     gb.p[i] = p;
   }
   DZ_TRY(run_nn("conv1_fwd", gb, false, stream));
+  if (gb.p[0].splits > 1) DZ_TRY(finish_nn(gb, outs1, false, stream));
   // conv2 / conv3: few output tiles (41 / 25 per pass) -> split K four ways so the grid covers the 148 SMs;
   // finish_nn adds the bias and ReLU.
   for (int layer = 2; layer <= 3; ++layer) {
