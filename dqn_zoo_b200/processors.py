@@ -128,6 +128,12 @@ class BatchedAtariPreprocessor:
         int(bv[min(y0 + self._band_rows, oh) - 1].sum() - bv[y0, 0]) for y0 in range(0, oh, self._band_rows))
     # only the last two slots of the action-repeat buffer are ever pooled (processors.py:485)
     self._raw = torch.zeros((self._n, 2, h, w, 3), dtype=torch.uint8, device=self._device)
+    # one pinned staging area + one H2D copy per tick and pooled slot instead of one copy per stream
+    self._stage = [torch.zeros((self._n, h, w, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    self._stage_np = [t.numpy() for t in self._stage]
+    self._stage_dev = torch.zeros((self._n, h, w, 3), dtype=torch.uint8, device=self._device) if self._n > 1 else None
+    self._stage_done = [torch.cuda.Event() for _ in range(2)]
+    self._stage_pending = [False, False]
     self._stacks = torch.zeros((self._n, oh, ow, self._stack), dtype=torch.uint8, device=self._device)
     self._meta_host = torch.zeros((4, self._n), dtype=torch.int64).pin_memory()
     self._meta = torch.zeros((4, self._n), dtype=torch.int64, device=self._device)
@@ -152,6 +158,7 @@ class BatchedAtariPreprocessor:
       raise ValueError('expected %d timesteps' % self._n)
     emit = []
     scalars = [None] * self._n
+    uploads = ([], [])                          # per pooled slot: streams whose new frame goes there this tick
     for e, ts in enumerate(timesteps):
       if ts is None:
         continue
@@ -175,12 +182,19 @@ class BatchedAtariPreprocessor:
         frame = np.ascontiguousarray(rgb, dtype=np.uint8)
         if frame.shape != self._in_shape:
           raise ValueError('frame shape changed: %s vs %s' % (frame.shape, self._in_shape))
-        self._raw[e, pooled_slot].copy_(torch.from_numpy(frame), non_blocking=False)
+        if self._stage_pending[pooled_slot] and not uploads[pooled_slot]:
+          self._stage_done[pooled_slot].synchronize()        # the previous copy out of this staging area has finished
+          self._stage_pending[pooled_slot] = False
+        np.copyto(self._stage_np[pooled_slot][len(uploads[pooled_slot])], frame)
+        uploads[pooled_slot].append(e)
         st.has_frame[st.index] = True
       st.index += 1
       if self._should_emit(st):
         scalars[e] = self._reduce_scalars(st)
         emit.append(e)
+    for slot in (0, 1):
+      if uploads[slot]:
+        self._upload(slot, uploads[slot])
     if emit:
       self._launch(emit)
     outs = [None] * self._n
@@ -190,6 +204,22 @@ class BatchedAtariPreprocessor:
       obs = self._stacks[e].clone() if self._device_obs else self._stacks[e].cpu().numpy()
       outs[e] = parts.TimeStep(step_type=step_type, reward=reward, discount=discount, observation=obs)
     return outs
+
+  def _upload(self, slot, streams):
+    """Staged frames [0, k) of `slot` -> raw[streams, slot]: one async H2D, then (if needed) one device scatter."""
+    k = len(streams)
+    src = self._stage[slot][:k]
+    if k == self._n and streams == list(range(k)):
+      self._raw[:, slot].copy_(src, non_blocking=True)
+    elif k == 1:
+      self._raw[streams[0], slot].copy_(src[0], non_blocking=True)
+    else:
+      dev = self._stage_dev[:k]
+      dev.copy_(src, non_blocking=True)
+      index = torch.as_tensor(streams, dtype=torch.int64).to(self._device)
+      self._raw[:, slot].index_copy_(0, index, dev)
+    self._stage_done[slot].record()
+    self._stage_pending[slot] = True
 
   def _should_emit(self, st) -> bool:           # TimestepBufferCondition, processors.py:165-215
     if st.should_reset:
