@@ -119,3 +119,128 @@ def test_life_loss_zeroes_the_discount():
   p(po.FIRST, None, None, (f, 3))
   outs = [p(po.MID, 0.0, 1.0, (f, 3 if i != 2 else 2)) for i in range(4)]
   assert outs[3][2] == 0.0
+
+
+# ---- scalar half: the scenarios of processors_test.py, through the oracle AND the product's host state machine ----
+
+def _machines(**kwargs):
+  """(name, feed(step_type, reward, discount, lives) -> None | (type, reward, discount)) for both implementations.
+
+  The product class (dqn_zoo_b200.processors) only touches CUDA when it sees pixels; its emission rule and scalar
+  aggregation are plain host code and are driven here directly."""
+  from dqn_zoo_b200 import processors as dev
+
+  frame = np.zeros((8, 16, 3), np.uint8)
+  oracle = po.AtariPreprocessor(resize_shape=(4, 4), **kwargs)
+
+  def feed_oracle(st, r, d, lives=3):
+    out = oracle(st, r, d, (frame, lives))
+    return None if out is None else out[:3]
+
+  product = dev.BatchedAtariPreprocessor(num_streams=1, resize_shape=(4, 4), **kwargs)
+  stream = product._streams[0]
+
+  def feed_product(st, r, d, lives=3):
+    # the part of BatchedAtariPreprocessor.step() that precedes the pixel upload / kernel launch
+    if product._life_loss:
+      lost = st == po.MID and lives < stream.lives
+      stream.lives = lives
+      if lost:
+        d = 0.0
+    if stream.index >= product._repeats:
+      stream.index = 0
+      stream.slots = [None] * product._repeats
+    stream.slots[stream.index] = (dev.StepType(st), r, d)
+    stream.index += 1
+    if not product._should_emit(stream):
+      return None
+    t, rr, dd = product._reduce_scalars(stream)
+    return int(t), rr, dd
+
+  def reset_both():
+    oracle.reset()
+    stream.reset()
+
+  return [('oracle', feed_oracle), ('product', feed_product)], reset_both
+
+
+def test_emission_cadence_table():
+  """processors_test.py:74-93: F emits at once, then every 4th MID, and LAST emits immediately."""
+  machines, _ = _machines()
+  seq = [(0, True)] + [(1, False), (1, False), (1, False), (1, True)] * 2 + [(1, False), (2, True)]
+  for name, feed in machines:
+    for st, expected in seq:
+      out = feed(st, None if st == 0 else 0.0, None if st == 0 else 1.0)
+      assert (out is not None) == expected, (name, st)
+
+
+def test_errors_without_reset_and_with_two_boundaries():
+  """processors_test.py:95-137."""
+  for kwargs in ({}, {'num_action_repeats': 3}):
+    machines, _ = _machines(**kwargs)
+    for name, feed in machines:
+      feed(0, None, None)
+      feed(1, 0.0, 1.0)
+      feed(2, 0.0, 0.0)
+      with pytest.raises(RuntimeError, match='Should have reset'):
+        feed(0, None, None)
+  machines, _ = _machines(num_action_repeats=3)
+  for name, feed in machines:            # [F, M, F] inside one buffer
+    feed(0, None, None)                  # slot 2 -> emitted, buffer restarts
+    feed(0, None, None)                  # slot 0: a second FIRST without a LAST in between is accepted alone ...
+    feed(1, 0.0, 1.0)
+    with pytest.raises(RuntimeError, match='at most one FIRST or LAST'):
+      feed(2, 0.0, 0.0)                  # ... but FIRST and LAST in the same buffer are not
+
+
+@pytest.mark.parametrize('types,discounts,lives,expected', [
+    ('fmmmmm', 'n11111', '333333', 'n11111'),
+    ('fmmmmm', 'n11111', '333222', 'n11011'),
+    ('fmmmmm', 'n11111', '332211', 'n10101'),
+])
+def test_life_loss_zeroes_exactly_the_losing_step(types, discounts, lives, expected):
+  """processors_test.py:204-253 (ZeroDiscountOnLifeLoss), observed through the emitted discount products."""
+  machines, _ = _machines(num_action_repeats=2, additional_discount=1.0, max_abs_reward=None)
+  code = {'f': 0, 'm': 1, 'l': 2}
+  for name, feed in machines:
+    got = []
+    for t, d, lv in zip(types, discounts, lives):
+      out = feed(code[t], None if t == 'f' else 8.0, None if d == 'n' else float(d), int(lv))
+      if out is not None:
+        got.append(out[2])
+    # repeats of 2: emissions at f, then after each pair of m; the product over a pair is 0 iff a loss fell in it
+    want = [None]
+    per_step = [None if e == 'n' else float(e) for e in expected][1:]
+    for i in range(0, len(per_step) - 1, 2):
+      want.append(per_step[i] * per_step[i + 1])
+    assert got == want, (name, got, want)
+
+
+@pytest.mark.parametrize('rewards,clip,expected', [([1, 2, 3, 0], None, 6), ([1, -2, 3, 0], None, 2), ([1, 2, 3, 0], 2, 2),
+                                                   ([-1, -2, 0.5, 0], 2, -2), ([0.5, 0.2, 0, 0.1], 1.0, 0.8)])
+def test_reward_sum_then_clip(rewards, clip, expected):
+  """processors_test.py:281-349: rewards are summed over the action repeats, then clipped."""
+  machines, _ = _machines(max_abs_reward=clip)
+  for name, feed in machines:
+    feed(0, None, None)
+    out = None
+    for r in rewards:
+      out = feed(1, r, 1.0)
+    assert out is not None and out[0] == po.MID
+    assert out[1] == pytest.approx(expected), name
+    assert out[2] == pytest.approx(0.99)
+
+
+def test_first_has_no_reward_or_discount_and_last_is_reported():
+  """processors_test.py:255-279 (reduce_step_type) via the pipeline: 000F -> FIRST, MML0 -> LAST, MMMM -> MID."""
+  machines, _ = _machines()
+  for name, feed in machines:
+    out = feed(0, None, None)
+    assert out == (po.FIRST, None, None), name
+    for _ in range(3):
+      assert feed(1, 1.0, 1.0) is None
+    assert feed(1, 1.0, 1.0)[0] == po.MID
+    feed(1, 1.0, 1.0)
+    feed(1, 1.0, 1.0)
+    out = feed(2, 1.0, 0.0)
+    assert out[0] == po.LAST and out[2] == 0.0 and out[1] == 1.0   # 3 summed, clipped to 1
