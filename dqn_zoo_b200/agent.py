@@ -25,6 +25,7 @@ import numpy as np
 import torch
 
 from dqn_zoo_b200 import _lib
+from dqn_zoo_b200 import jax_prng
 from dqn_zoo_b200 import learner as learner_lib
 from dqn_zoo_b200 import parts
 from dqn_zoo_b200 import replay as replay_lib
@@ -144,6 +145,8 @@ class _DeviceAgent(parts.Agent):
     }
     if self.PRIORITIZED:
       state['max_seen_priority'] = self.max_seen_priority
+    if getattr(self, '_jax_key', None) is not None:
+      state['rng_key']['jax'] = self._jax_key.copy()
     return state
 
   def set_state(self, state: Mapping[str, Any]) -> None:
@@ -151,6 +154,8 @@ class _DeviceAgent(parts.Agent):
     self._host_rng.set_state(state['rng_key']['host'])
     self._seed = state['rng_key']['seed']
     self._learner.counters[1] = int(state['rng_key']['device_counter'])
+    if getattr(self, '_jax_key', None) is not None:
+      self._jax_key = np.asarray(state['rng_key']['jax'], dtype=np.uint32).copy()
     self._frame_t = state['frame_t']
     self._learner.set_opt_state(state['opt_state'])
     self._learner.set_params(state['online_params'], blob='online')
@@ -169,7 +174,13 @@ class _DeviceAgent(parts.Agent):
       self._obs_dev.copy_(torch.from_numpy(np.ascontiguousarray(obs).reshape(-1)))
     L = self._learner
     taus = noise = None
-    if self.KIND in ('iqn', 'rainbow'):
+    if getattr(self, '_jax_key', None) is not None:
+      # iqn/agent.py:220-222: rng_key, sample_key, apply_key, policy_key = split(rng_key, 4); tau_t = uniform(sample_key)
+      self._jax_key, sample = jax_prng.iqn_act_keys(self._jax_key)
+      self._jax_act.set_keys(sample)
+      self._jax_act.launch(L.taus)
+      taus = L.taus
+    elif self.KIND in ('iqn', 'rainbow'):
       L.generate_randomness(self._seed)
       taus = L.taus if self.KIND == 'iqn' else None
       noise = L.noise if self.KIND == 'rainbow' else None
@@ -215,6 +226,10 @@ class _DeviceAgent(parts.Agent):
   def _learn(self) -> None:
     """rainbow/agent.py:181-198 as one enqueue."""
     slot = self._draws()
+    if getattr(self, '_jax_key', None) is not None:
+      # iqn/agent.py:207 + 182: the agent key advances once per update; three sample keys feed the tau draws
+      self._jax_key, sample = jax_prng.iqn_update_keys(self._jax_key)
+      self._jax_learn.set_keys(sample)
     self._stage_dev.copy_(slot, non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()
@@ -264,7 +279,9 @@ class _DeviceAgent(parts.Agent):
 
   def _enqueue(self):
     L = self._learner
-    if self.KIND in ('iqn', 'rainbow'):
+    if getattr(self, '_jax_key', None) is not None:
+      self._jax_learn.launch(L.taus)            # jax.random.uniform draws from the keys staged by _learn()
+    elif self.KIND in ('iqn', 'rainbow'):
       L.generate_randomness(self._seed)
     L.learn(self._view, self.PRIORITIZED, self._io)
 
@@ -374,13 +391,26 @@ class Iqn(_DeviceAgent):
   def __init__(self, preprocessor, sample_network_input, network, optimizer, transition_accumulator, replay,
                batch_size, exploration_epsilon, min_replay_capacity_fraction, learn_period,
                target_network_update_period, huber_param, tau_samples_policy, tau_samples_s_tm1, tau_samples_s_t,
-               rng_key, use_cuda_graph=True):
+               rng_key, use_cuda_graph=True, jax_prng_taus=False):
+    """`jax_prng_taus=True`: `rng_key` is treated as a jax PRNG key (`jax.random.PRNGKey(seed)` = [0, seed]) and the tau
+    samples of every update and every action selection follow the reference's key chain bit for bit
+    (iqn/agent.py:182-190, 207, 220-222; threefry2x32 + jax.random.split/uniform, csrc/dz_jaxprng.cu).  The default keeps
+    the device Philox stream.  Epsilon-greedy exploration uses a host RandomState either way."""
     if (network.tau_samples_policy, network.tau_samples_s_tm1, network.tau_samples_s_t) != (
         tau_samples_policy, tau_samples_s_tm1, tau_samples_s_t):
       raise ValueError('tau sample counts must match the NetworkSpec')
     self._setup(preprocessor, sample_network_input, network, optimizer, transition_accumulator, replay, batch_size,
                 exploration_epsilon, min_replay_capacity_fraction, learn_period, target_network_update_period, rng_key,
                 huber_param=huber_param, use_cuda_graph=use_cuda_graph)
+    if jax_prng_taus:
+      key = np.asarray(rng_key, dtype=np.uint32).reshape(-1)
+      if key.size != 2:
+        raise ValueError('jax_prng_taus needs a jax-style rng_key of two uint32 words')
+      self._jax_key = key.copy()
+      dev = self._learner.device
+      self._jax_learn = jax_prng.DeviceUniform([batch_size * tau_samples_s_tm1, batch_size * tau_samples_policy,
+                                                batch_size * tau_samples_s_t], dev)
+      self._jax_act = jax_prng.DeviceUniform([tau_samples_policy], dev)
 
 
 def _check_support(support, network):

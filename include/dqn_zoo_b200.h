@@ -330,6 +330,15 @@ int dz_atari_preprocess(const uint8_t* const* d_frame_a, const uint8_t* const* d
                         int32_t max_band_rows, void* stream);
 int32_t dz_atari_preprocess_band_rows(void);
 
+/* ---- JAX-compatible uniform draws -----------------------------------------------------------
+ * jax.random.uniform(key, (count,), float32) for up to 4 independent keys per launch, bit-identical to jax 0.3.10's
+ * threefry2x32 path (iqn/agent.py:45-50 `_sample_tau`).  d_keys: DEVICE uint32 [nblocks][2] (so that a captured CUDA
+ * graph can be replayed with fresh keys); counts: HOST int64 [nblocks]; block b is written at
+ * d_out + sum(counts[:b]). */
+int dz_jax_uniform(const uint32_t* d_keys, const int64_t* counts, int32_t nblocks, float* d_out, void* stream);
+/* threefry2x32 (20 rounds) evaluated on the HOST by the same source the kernel compiles; tests only. */
+int dz_test_threefry2x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t* out2);
+
 /* Device pointer + element count of an internal learner buffer ("act3", "h1", "dh1", "iqn_hi", "iqn_dhi");
  * tests/tools only. */
 int dz_test_learner_buffer(dz_learner* l, const char* name, float** d_ptr, int64_t* count);
