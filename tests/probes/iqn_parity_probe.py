@@ -1,8 +1,9 @@
 """Prints the per-tensor gradient error of the IQN learner against the CPU oracle (84x84, B=32, 64 taus),
 twice per configuration (bitwise repeatability), for several accumulation-run lengths / stream settings."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, _ROOT)
+sys.path.insert(0, os.path.join(_ROOT, 'tests'))
 import numpy as np, torch
 import test_gpu_learner as T
 

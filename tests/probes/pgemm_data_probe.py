@@ -1,7 +1,8 @@
 """Runs the packed tcgen05 GEMM self-test on the ACTUAL operands of the IQN fc1 backward pass."""
 import sys, os, ctypes as C
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, _ROOT)
+sys.path.insert(0, os.path.join(_ROOT, 'tests'))
 import numpy as np, torch
 import test_gpu_learner as T
 import test_gpu_tc as G
