@@ -8,13 +8,7 @@ import torch
 
 from oracle import jax_prng_oracle as jo
 
-import os
-
-# Written after the round's GPU budget was spent: the arithmetic is verified on the CPU (host-compiled threefry2x32 and
-# the host key handling vs the KAT-pinned oracle, tests/test_jax_prng.py) but these two device tests have not run on a
-# B200 yet, so they are opt-in until they have (DZ_RUN_UNVALIDATED=1).
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('DZ_RUN_UNVALIDATED') != '1', reason='device path not yet validated on a GPU')]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize('counts', [[1], [2], [5], [2048], [2047, 3, 64], [64, 2048, 1, 7]])
