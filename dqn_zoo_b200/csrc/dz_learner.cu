@@ -17,6 +17,7 @@
 
 #include "dz_tc.cuh"
 #include "dz_internal.cuh"
+#include "dz_umma_net.cuh"
 
 namespace dz {
 
@@ -990,6 +991,10 @@ struct dz_learner {
   cudaStream_t side;
   cudaEvent_t ev_fork, ev_join;
   bool side_dirty;
+  // TMA-fed tcgen05 path of the batch-sized step (dz_umma_net.cu): torso + 3136 -> 512 layer(s), forward and input gradients
+  UmNet* um;
+  char* um_ws;
+  int um_npass, um_set[3];
 };
 
 namespace {
@@ -1015,6 +1020,13 @@ int pick_splits(int64_t tiles, int nkb, int max_splits) {
   }
   return best;
 }
+
+// DZ_UMMA=0 keeps every contraction on the fp32-FMA kernels (A/B timing, geometries the tcgen05 path does not cover).
+bool g_umma = true;
+int64_t noise_stride(const dz_learner_config& c, const Dims& d);
+struct NoiseVecs;
+
+UmNetDesc make_um_desc(const dz_learner* l);
 
 int64_t carve(dz_learner* l, char* base) {
   const dz_learner_config& c = l->cfg;
@@ -1110,6 +1122,15 @@ int64_t carve(dz_learner* l, char* base) {
   l->s_d = w.take<float>(B);
   l->s_w = w.take<float>(B);
   l->q_scratch = w.take<float>(64);
+  l->um_ws = nullptr;
+  if (g_umma) {
+    UmNetDesc ud = make_um_desc(l);
+    if (um_net_supported(ud)) {
+      int64_t bytes = um_net_workspace_bytes(ud);
+      l->um_ws = w.take<char>(bytes);
+      if (!base) l->um_ws = reinterpret_cast<char*>(1);   // size query: "enabled" marker only
+    }
+  }
   return w.used;
 }
 
@@ -1126,6 +1147,42 @@ NoiseVecs noise_of(const dz_learner_config& c, const Dims& d, const float* base,
   n.a1i = p; p += pad4(d.feat); n.a1o = p; p += 512; n.a2i = p; p += 512; n.a2o = p; p += pad4((int64_t)c.num_actions * c.num_atoms);
   n.v1i = p; p += pad4(d.feat); n.v1o = p; p += 512; n.v2i = p; p += 512; n.v2o = p;
   return n;
+}
+
+UmNetDesc make_um_desc(const dz_learner* l) {
+  const dz_learner_config& c = l->cfg;
+  const Dims& d = l->d;
+  const Layout& L = l->lay;
+  UmNetDesc u;
+  memset(&u, 0, sizeof(u));
+  const bool needs_online_st = c.kind == DZ_DOUBLE_Q || c.kind == DZ_PRIORITIZED || c.kind == DZ_RAINBOW;
+  u.B = c.batch; u.H = d.H; u.W = d.W;
+  u.npass = needs_online_st ? 3 : 2;
+  u.pass_target[0] = 0; u.pass_target[1] = needs_online_st ? 0 : 1; u.pass_target[2] = 1;
+  u.online = l->buf.d_online; u.target = l->buf.d_target;
+  const char* cw[3] = {"conv1/w", "conv2/w", "conv3/w"};
+  const char* cb[3] = {"conv1/b", "conv2/b", "conv3/b"};
+  for (int i = 0; i < 3; ++i) { u.off_conv_w[i] = L.off(cw[i]); u.off_conv_b[i] = L.off(cb[i]); }
+  u.use_fc = c.kind != DZ_IQN;
+  u.nstream = c.kind == DZ_RAINBOW ? 2 : 1;
+  u.noisy = c.kind == DZ_RAINBOW ? 1 : 0;
+  if (c.kind == DZ_RAINBOW) {
+    const char* st[2] = {"adv", "val"};
+    for (int s = 0; s < 2; ++s) {
+      std::string pre = std::string(st[s]) + "1/";
+      u.off_fc_w[s] = L.off(pre + "mu/w"); u.off_fc_b[s] = L.off(pre + "mu/b");
+      u.off_fc_sw[s] = L.off(pre + "sigma/w"); u.off_fc_sb[s] = L.off(pre + "sigma/b");
+    }
+    static float origin[1];
+    NoiseVecs nz = noise_of(c, d, origin, 0);
+    u.noise_stride = noise_stride(c, d);
+    u.noise_off_in[0] = nz.a1i - origin; u.noise_off_out[0] = nz.a1o - origin;
+    u.noise_off_in[1] = nz.v1i - origin; u.noise_off_out[1] = nz.v1o - origin;
+    for (int p = 0; p < 3; ++p) u.noise_apply[p] = p;
+  } else if (u.use_fc) {
+    u.off_fc_w[0] = L.off("fc1/w"); u.off_fc_b[0] = L.off("fc1/b");
+  }
+  return u;
 }
 
 GemmProblem zero_problem() {
@@ -1170,6 +1227,7 @@ void read_env() {
   g_pk_iqn = !(getenv("DZ_PK_IQN") != nullptr && std::string(getenv("DZ_PK_IQN")) == "0");
   g_fc_splits = getenv("DZ_FC_SPLITS") ? atoi(getenv("DZ_FC_SPLITS")) : 0;
   g_conv1_splits = getenv("DZ_CONV1_SPLITS") ? atoi(getenv("DZ_CONV1_SPLITS")) : 1;
+  g_umma = !(getenv("DZ_UMMA") != nullptr && std::string(getenv("DZ_UMMA")) == "0");
 }
 
 bool tc_enabled_for(const char* tag) {
@@ -1465,7 +1523,7 @@ int forward_torso(dz_learner* l, const TorsoJob* jobs, int njobs, int nimg, void
 }
 
 // Heads for the dqn / double_q / prioritized / c51 / qrdqn family.
-int forward_heads_plain(dz_learner* l, const Pass* passes, int np, int nimg, void* stream) {
+int forward_heads_plain(dz_learner* l, const Pass* passes, int np, int nimg, void* stream, bool fc1_done = false) {
   const Dims& d = l->d;
   const Layout& L = l->lay;
   GemmBatch gb;
@@ -1473,7 +1531,7 @@ int forward_heads_plain(dz_learner* l, const Pass* passes, int np, int nimg, voi
   float* outs[kMaxProblems];
   const bool shared = l->cfg.kind == DZ_DOUBLE_Q || l->cfg.kind == DZ_PRIORITIZED;
   const int splits = nimg <= 32 ? l->fc_splits : 1;
-  for (int i = 0; i < np; ++i) {
+  for (int i = 0; i < np && !fc1_done; ++i) {
     GemmProblem p = zero_problem();
     p.a_mode = A_PLAIN; p.A = l->act3[passes[i].set]; p.lda = d.feat; p.M = nimg; p.K = d.feat;
     p.B = passes[i].params + L.off("fc1/w"); p.N = 512; p.ldb = 512; p.ldc = 512;
@@ -1487,8 +1545,10 @@ int forward_heads_plain(dz_learner* l, const Pass* passes, int np, int nimg, voi
     }
     gb.p[i] = p;
   }
-  DZ_TRY(run_nn("fc1_fwd", gb, false, stream));
-  if (splits > 1) DZ_TRY(finish_nn(gb, outs, false, stream));
+  if (!fc1_done) {
+    DZ_TRY(run_nn("fc1_fwd", gb, false, stream));
+    if (splits > 1) DZ_TRY(finish_nn(gb, outs, false, stream));
+  }
   for (int i = 0; i < np; ++i) {
     GemmProblem p = zero_problem();
     p.a_mode = A_PLAIN; p.A = l->h1[passes[i].head][0]; p.lda = 512; p.M = nimg; p.K = 512;
@@ -1509,7 +1569,7 @@ int forward_heads_plain(dz_learner* l, const Pass* passes, int np, int nimg, voi
 }
 
 // Rainbow: two noisy streams (networks.py:224-261, :137-178).
-int forward_heads_rainbow(dz_learner* l, const Pass* passes, int np, int nimg, const float* noise, void* stream) {
+int forward_heads_rainbow(dz_learner* l, const Pass* passes, int np, int nimg, const float* noise, void* stream, bool fc1_done = false) {
   const Dims& d = l->d;
   const Layout& L = l->lay;
   const dz_learner_config& c = l->cfg;
@@ -1519,7 +1579,7 @@ int forward_heads_rainbow(dz_learner* l, const Pass* passes, int np, int nimg, c
   float* outs[kMaxProblems];
   const int splits = nimg <= 32 ? l->fc_splits : 1;
   const char* st[2] = {"adv", "val"};
-  for (int i = 0; i < np; ++i) {
+  for (int i = 0; i < np && !fc1_done; ++i) {
     NoiseVecs nz = noise_of(c, d, noise, passes[i].apply);
     for (int s = 0; s < 2; ++s) {
       std::string pre = std::string(st[s]) + "1/";
@@ -1540,8 +1600,10 @@ int forward_heads_rainbow(dz_learner* l, const Pass* passes, int np, int nimg, c
       gb.p[q] = p;
     }
   }
-  DZ_TRY(run_nn("noisy1_fwd", gb, true, stream));
-  if (splits > 1) DZ_TRY(finish_nn(gb, outs, true, stream));
+  if (!fc1_done) {
+    DZ_TRY(run_nn("noisy1_fwd", gb, true, stream));
+    if (splits > 1) DZ_TRY(finish_nn(gb, outs, true, stream));
+  }
   for (int i = 0; i < np; ++i) {
     NoiseVecs nz = noise_of(c, d, noise, passes[i].apply);
     for (int s = 0; s < 2; ++s) {
@@ -1754,6 +1816,7 @@ int backward_torso(dz_learner* l, const uint8_t* const* rows0, void* stream) {
   FinishTNBatch fb;
   fb.n = 0;
   GemmBatch gb;
+  if (l->um && l->cfg.kind == DZ_IQN) DZ_TRY(um_split_dact3(l->um, stream));   // dact3 came from the Hadamard kernel (fp32)
   // conv3 wgrad
   {
     GemmProblem p = zero_problem();
@@ -1767,7 +1830,9 @@ int backward_torso(dz_learner* l, const uint8_t* const* rows0, void* stream) {
     fb.f[fb.n++] = FinishTN{p.C, splits, p.split_stride, p.K, 64, G + L.off("conv3/w"), nullptr, p.Cb, nullptr, nullptr, nullptr};
   }
   // conv3 dgrad: dcol = dpre3 * W3^T ; col2im with ReLU mask of act2
-  {
+  if (l->um) {
+    DZ_TRY(um_backward_conv3(l->um, stream));
+  } else {
     GemmProblem p = zero_problem();
     p.A = l->dact3; p.lda = 64; p.M = B * d.h3 * d.w3; p.N = 64; p.K = 576;
     p.B = P + L.off("conv3/w"); p.ldb = 64; p.C = l->dcol; p.ldc = 576;
@@ -1790,7 +1855,9 @@ int backward_torso(dz_learner* l, const uint8_t* const* rows0, void* stream) {
     fb.f[fb.n++] = FinishTN{p.C, splits, p.split_stride, p.K, 64, G + L.off("conv2/w"), nullptr, p.Cb, nullptr, nullptr, nullptr};
   }
   // conv2 dgrad
-  {
+  if (l->um) {
+    DZ_TRY(um_backward_conv2(l->um, stream));
+  } else {
     GemmProblem p = zero_problem();
     p.A = l->dact2; p.lda = 64; p.M = B * d.h2 * d.w2; p.N = 64; p.K = 512;
     p.B = P + L.off("conv2/w"); p.ldb = 64; p.C = l->dcol; p.ldc = 512;
@@ -1851,7 +1918,10 @@ int backward_plain(dz_learner* l, void* stream) {
     gb.p[0] = p;
     DZ_TRY(run_tn("fc1_wgrad", gb, fork_side(l, stream)));
   }
-  {  // dact3 = dh1 * Wf^T, masked by act3 > 0
+  if (l->um) {   // dact3 on the tcgen05 path: dh1 -> tf32 hi/lo, W streamed once through TMA, split partials + masked finish
+    DZ_TRY(um_split_dh1(l->um, stream));
+    DZ_TRY(um_backward_fc(l->um, nullptr, stream));
+  } else {  // dact3 = dh1 * Wf^T, masked by act3 > 0
     GemmProblem p = zero_problem();
     p.A = l->dh1[0]; p.lda = 512; p.M = B; p.N = 512; p.K = d.feat;
     p.B = P + L.off("fc1/w"); p.ldb = 512; p.ldc = d.feat;
@@ -1910,6 +1980,11 @@ int backward_rainbow(dz_learner* l, const float* noise, void* stream) {
     gb.p[s] = p;
   }
   DZ_TRY(run_tn("noisy1_wgrad", gb, fork_side(l, stream)));
+  if (l->um) {
+    DZ_TRY(um_split_dh1(l->um, stream));
+    DZ_TRY(um_backward_fc(l->um, noise, stream));
+    return DZ_OK;
+  }
   for (int s = 0; s < 2; ++s) {  // dact3 contributions
     std::string pre = std::string(st[s]) + "1/";
     GemmProblem p = zero_problem();
@@ -2087,7 +2162,17 @@ int update_impl(dz_learner* l, const dz_batch* batch, const dz_update_outputs* o
   jobs[nj++] = TorsoJob{on, batch->d_s_tm1_rows, 0};
   if (needs_online_st) jobs[nj++] = TorsoJob{on, batch->d_s_t_rows, 1};
   jobs[nj++] = TorsoJob{tg, batch->d_s_t_rows, 2};
-  DZ_TRY(forward_torso(l, jobs, nj, B, stream));
+  const bool um = l->um != nullptr;
+  if (um) {
+    if (nj != l->um_npass) return fail(DZ_EINVAL, "tcgen05 path: pass count mismatch");
+    const uint8_t* const* rows[3] = {nullptr, nullptr, nullptr};
+    for (int i = 0; i < nj; ++i) rows[i] = jobs[i].rows;
+    DZ_TRY(um_pack_weights(l->um, stream));
+    DZ_TRY(um_forward_torso(l->um, rows, stream));
+    if (c.kind != DZ_IQN) DZ_TRY(um_forward_fc(l->um, batch->d_noise, stream));
+  } else {
+    DZ_TRY(forward_torso(l, jobs, nj, B, stream));
+  }
 
   if (c.kind == DZ_IQN) {
     // online(s_tm1, tau_tm1) | target(s_t, tau_selector) | target(s_t, tau_t)   (iqn/agent.py:192-203)
@@ -2099,14 +2184,14 @@ int update_impl(dz_learner* l, const dz_batch* batch, const dz_update_outputs* o
     DZ_TRY(forward_heads_iqn(l, passes, 3, B, taus, true, stream));
   } else if (c.kind == DZ_RAINBOW) {
     Pass passes[3] = {{on, nullptr, 0, 0, 0}, {on, nullptr, 1, 1, 1}, {tg, nullptr, 2, 2, 2}};
-    DZ_TRY(forward_heads_rainbow(l, passes, 3, B, batch->d_noise, stream));
+    DZ_TRY(forward_heads_rainbow(l, passes, 3, B, batch->d_noise, stream, um));
   } else {
     Pass passes[3];
     int np = 0;
     passes[np++] = Pass{on, nullptr, 0, 0, 0};
     if (needs_online_st) passes[np++] = Pass{on, nullptr, 1, 1, 0};
     passes[np++] = Pass{tg, nullptr, 2, 2, 0};
-    DZ_TRY(forward_heads_plain(l, passes, np, B, stream));
+    DZ_TRY(forward_heads_plain(l, passes, np, B, stream, um));
   }
 
   // ---- loss + gradient wrt the pass-0 head outputs
@@ -2159,6 +2244,8 @@ extern "C" {
 int dz_learner_plan_query(const dz_learner_config* cfg, dz_learner_plan* out) {
   DZ_TRY(validate(*cfg));
   dz_learner tmp;
+  tmp.um = nullptr;
+  memset(&tmp.buf, 0, sizeof(tmp.buf));
   tmp.cfg = *cfg;
   tmp.lay = make_layout(*cfg);
   tmp.d = make_dims(*cfg);
@@ -2198,7 +2285,25 @@ int dz_learner_create(const dz_learner_config* cfg, const dz_learner_buffers* bu
   l->lay = make_layout(*cfg);
   l->d = make_dims(*cfg);
   l->B = cfg->batch;
+  l->um = nullptr;
   carve(l, static_cast<char*>(buf->d_workspace));
+  if (l->um_ws) {
+    UmNetDesc ud = make_um_desc(l);
+    int rc = um_net_create(ud, l->um_ws, &l->um);
+    if (rc != DZ_OK) { delete l; return rc; }
+    const bool three = ud.npass == 3;
+    l->um_npass = ud.npass;
+    l->um_set[0] = 0; l->um_set[1] = three ? 1 : 2; l->um_set[2] = 2;
+    for (int i = 0; i < ud.npass; ++i) {   // the fp32 views the remaining FMA kernels, the losses and the tests read
+      const int set = l->um_set[i];
+      l->act1[set] = um_act_f32(l->um, 1, i); l->act2[set] = um_act_f32(l->um, 2, i); l->act3[set] = um_act_f32(l->um, 3, i);
+      if (ud.use_fc)
+        for (int s = 0; s < ud.nstream; ++s) l->h1[set][s] = um_h1_f32(l->um, i, s);
+    }
+    if (ud.use_fc)
+      for (int s = 0; s < ud.nstream; ++s) l->dh1[s] = um_dh1_f32(l->um, s);
+    l->dact3 = um_dact_f32(l->um, 3); l->dact2 = um_dact_f32(l->um, 2); l->dact1 = um_dact_f32(l->um, 1);
+  }
   l->side = nullptr; l->ev_fork = nullptr; l->ev_join = nullptr; l->side_dirty = false;
   if (getenv("DZ_NO_SIDE_STREAM") == nullptr) {
     if (cudaStreamCreateWithFlags(&l->side, cudaStreamNonBlocking) != cudaSuccess ||
@@ -2232,6 +2337,7 @@ int dz_learner_create(const dz_learner_config* cfg, const dz_learner_buffers* bu
 
 void dz_learner_destroy(dz_learner* l) {
   if (!l) return;
+  um_net_destroy(l->um);
   if (l->side) { cudaStreamSynchronize(l->side); cudaStreamDestroy(l->side); }
   if (l->ev_fork) cudaEventDestroy(l->ev_fork);
   if (l->ev_join) cudaEventDestroy(l->ev_join);

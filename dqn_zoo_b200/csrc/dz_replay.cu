@@ -384,18 +384,19 @@ __global__ void __launch_bounds__(256) gather_obs_kernel(dz_replay_view v, const
                                                          uint8_t* __restrict__ s_tm1, uint8_t* __restrict__ s_t,
                                                          int vec16) {
   dz::pdl_enter();
-  const int b = blockIdx.y >> 1, which = blockIdx.y & 1;
+  // the row index rides on grid.x (2^31 - 1 blocks); grid.y is only the <= 8-way split of one row
+  const int b = blockIdx.x >> 1, which = blockIdx.x & 1;
   const uint8_t* src = v.d_obs + (slots[b] * 2 + which) * v.obs_stride;
   uint8_t* dst = (which ? s_t : s_tm1) + (int64_t)b * v.obs_bytes;
   if (vec16) {
     const int64_t nvec = v.obs_bytes >> 4;
     const uint4* s4 = reinterpret_cast<const uint4*>(src);
     uint4* d4 = reinterpret_cast<uint4*>(dst);
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x)
+    for (int64_t i = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.y * blockDim.x)
       d4[i] = __ldg(s4 + i);
   } else {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < v.obs_bytes;
-         i += (int64_t)gridDim.x * blockDim.x)
+    for (int64_t i = blockIdx.y * (int64_t)blockDim.x + threadIdx.x; i < v.obs_bytes;
+         i += (int64_t)gridDim.y * blockDim.x)
       dst[i] = src[i];
   }
 }
@@ -488,8 +489,10 @@ __global__ void fill_scalars_kernel(dz_replay_view v, int64_t row0, int64_t n, u
 
 int launch_sample(const dz_replay_view* view, int prioritized, const dz_sample_inputs* in, const dz_sample_outputs* out,
                   int batch, const BatchExtras& ex, void* stream) {
-  if (batch <= 0 || batch > 1024) return fail(DZ_EINVAL, "batch must be in [1,1024]");
+  if (batch <= 0) return fail(DZ_EINVAL, "batch must be positive");
   if (prioritized) {
+    // one block: the importance weights are normalised by the batch maximum (replay.py:237-238)
+    if (batch > 1024) return fail(DZ_EINVAL, "prioritized batch must be in [1,1024]");
     if (!view->d_tree || !view->d_live || !view->d_id_at) return fail(DZ_EINVAL, "prioritized view lacks tree/live/id_at");
     if (!out->d_indices || !out->d_ids || !out->d_slots || !out->d_probs || !out->d_weights)
       return fail(DZ_EINVAL, "prioritized sample needs all outputs");
@@ -639,7 +642,7 @@ int dz_replay_gather(const dz_replay_view* view, const int64_t* d_slots, int32_t
   int vec16 = (view->obs_bytes % 16 == 0) && ((uintptr_t)d_s_tm1 % 16 == 0) && ((uintptr_t)d_s_t % 16 == 0);
   int64_t work = vec16 ? view->obs_bytes >> 4 : view->obs_bytes;
   int gx = (int)(ceil_div(work, 256) < 8 ? ceil_div(work, 256) : 8);
-  dim3 grid(gx, batch * 2);
+  dim3 grid((unsigned)batch * 2u, gx);
   DZ_LAUNCH(gather_obs_kernel, grid, 256, 0, stream, *view, d_slots, d_s_tm1, d_s_t, vec16);
   DZ_LAUNCH(gather_scalars_kernel, (int)ceil_div(batch, 128), 128, 0, stream, *view, d_slots, batch, d_a, d_r, d_disc);
   return DZ_OK;

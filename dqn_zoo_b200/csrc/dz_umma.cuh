@@ -1,0 +1,364 @@
+// TMA-fed tcgen05 GEMM family for the batch-32 learner step (sm_100a): every conv / 512-wide FC contraction of
+// networks.py:181-221 (dqn_torso, dqn_value_head) and :137-178 (noisy_linear), forward and input-gradient, as
+//
+//     D[i, j] = sum_r A(i, r) * B(j, r)          fp32 in, fp32-grade out (error-compensated 3xTF32)
+//
+// Operand tiles live in shared memory in the canonical 128-byte-swizzle UMMA layouts and are delivered by TMA
+// (cp.async.bulk.tensor, SWIZZLE_128B tensor maps) straight from the tensors' natural layouts:
+//
+//   K-major  (reduction index contiguous in the source): a stage is [rows][32 r] = rows x 128 B; convolutions get
+//            their implicit im2col from the tensor map itself — a box over (channels, ox, oy, image) of the NHWC
+//            activation lands as dense 128-byte rows, negative / out-of-range coordinates are zero-filled by the TMA
+//            unit (that is the zero padding of the input-gradient convolutions).
+//   MN-major (row index contiguous in the source, e.g. W[k][n] for y = xW): a stage is [32 r][32 mn] slabs, LBO
+//            apart; the instruction descriptor's major bit does the transposition — no shuffles, no transposed copies.
+//
+// Precision: activations are stored ONCE as tf32 hi/lo pairs by the producing epilogue (x = hi + lo, both exactly
+// representable), fp32 weights are split in place in shared memory by converter warps (raw tile -> hi in place, lo
+// in the sibling buffer; the split is position-wise, so it is swizzle-agnostic), D += Al*Bh + Ah*Bl + Ah*Bh.  The
+// tensor core truncates its fp32 accumulator (measured, dz_tcp.cuh), so accumulation runs are short (run_stages)
+// and are drained into registers with round-to-nearest adds while the next run fills the other TMEM buffer.
+//
+// The TMA "program" of every CTA (which boxes of which tensor map go where in each stage) is a table built once on
+// the host (dz_umma.cu): the device side is geometry-free.
+#pragma once
+#include <cuda.h>
+
+#include "dz_internal.cuh"
+#include "dz_tc.cuh"
+
+namespace dz {
+
+struct UmTmaOp {          // one TMA box load of one stage (32 bytes)
+  uint32_t map;           // index into the tensor-map array
+  uint32_t smem_off;      // byte offset inside the stage
+  int32_t c[5];           // box start coordinates (innermost first)
+  uint32_t pad;
+};
+
+struct UmOperand {
+  uint32_t part_bytes;    // bytes of one part (hi or lo) of a stage; multiple of 1024
+  uint32_t nparts;        // 2: hi + lo;  1: exact operand (values are tf32 numbers, no lo part)
+  uint32_t convert;       // 1: TMA delivers raw fp32 into part 0; converter warps split it into hi (in place) / lo (part 1)
+  uint32_t mn_major;      // 0: K-major [rows][32 r];  1: MN-major slabs of [r rows][32 mn]
+  uint32_t lbo;           // MN-major: bytes between 32-wide slabs (= r rows per stage * 128)
+  uint32_t kstep;         // bytes added to the descriptor start per MMA k-step of 8 (K-major 32, MN-major 1024)
+  const float* scale_r;   // convert only: element *= scale_r[reduction index] before the split (noisy sigma weights)
+};
+
+enum : uint32_t { UM_EPI_PARTIAL = 0, UM_EPI_ROWS = 1 };
+
+struct UmProblem {
+  UmOperand A, B;
+  uint32_t ksteps;          // MMA k-steps per stage
+  uint32_t run_stages;      // stages per accumulation run
+  uint32_t red_per_stage;   // reduction elements per stage
+  uint32_t epi;
+  int32_t MI, NJ;           // valid extents of D
+  // UM_EPI_PARTIAL: C[split * split_stride + i * sc_i + j * sc_j] = acc * (scale_i ? scale_i[i] : 1)
+  float* C;
+  long long sc_i, sc_j, split_stride;
+  const float* scale_i;
+  // UM_EPI_ROWS: one D row = one pixel / sample with NJ channels:
+  //   v = acc (+ bias[j]) (relu) (mask[dst * out_ld + j] > 0 ? v : 0)  ->  out_hi / out_lo (tf32 split) and out_f32
+  float* out_hi; float* out_lo; float* out_f32;
+  const float* bias;
+  const float* mask;
+  int32_t relu;
+  int32_t out_ld;           // floats between consecutive dst rows of out_* / mask (>= NJ; the pointers may be column-offset)
+  int32_t pw;               // tile row r -> (r / pw, r % pw); dst row = row_base + (r / pw) * rs_outer + (r % pw) * rs_inner
+  int32_t rs_outer, rs_inner;
+};
+
+struct UmCta {              // one per CTA
+  uint32_t prob;
+  uint32_t op0;             // first UmTmaOp
+  uint32_t nstages;
+  uint32_t ops_per_stage;
+  uint32_t tx_bytes;        // bytes landing per stage
+  int32_t r0;               // reduction index of stage 0 (for scale_r)
+  int32_t i0;               // UM_EPI_PARTIAL: first D row of this tile
+  int32_t split;
+  int32_t row_base;         // UM_EPI_ROWS
+  int32_t ph_valid, pw_valid;   // valid (r / pw) and (r % pw) extents
+  uint32_t pad;
+};
+
+namespace um {
+
+using namespace tc;
+
+constexpr int kStagesMax = 8;
+constexpr int kConvWarps = 8;
+constexpr int kThreadsU = (2 + 4 + kConvWarps) * 32;   // producer, mma, 4 epilogue, 8 converter warps
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst_smem, const void* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst_smem),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// 64-bit shared-memory matrix descriptor, SWIZZLE_128B canonical layouts (cute/arch/mma_sm100_desc.hpp):
+//   K-major : rows of 128 B, 8-row groups SBO = 1024 B apart, LBO unused
+//   MN-major: [8 r rows][128 B of mn] atoms; LBO = bytes between atoms along MN, SBO = bytes between 8-row groups along r
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;   // layout type SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+      "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+__device__ __forceinline__ void split4(const float4 x, float4& h, float4& l) {
+  h.x = rn_tf32(x.x); l.x = rn_tf32(x.x - h.x);
+  h.y = rn_tf32(x.y); l.y = rn_tf32(x.y - h.y);
+  h.z = rn_tf32(x.z); l.z = rn_tf32(x.z - h.z);
+  h.w = rn_tf32(x.w); l.w = rn_tf32(x.w - h.w);
+}
+
+// In-place hi/lo split of one raw operand part (a sequence of 128-byte swizzled rows).
+__device__ __forceinline__ void convert_part(const UmOperand& o, uint8_t* part0, int r0, int ct) {
+  const int nchunks = (int)(o.part_bytes >> 4);
+  const float* __restrict__ sc = o.scale_r;
+  const int rows_per_slab = (int)(o.lbo >> 7);
+  for (int idx = ct; idx < nchunks; idx += kConvWarps * 32) {
+    float4* p = reinterpret_cast<float4*>(part0 + ((size_t)idx << 4));
+    float4 x = *p;
+    if (sc) {
+      const int row = idx >> 3;
+      if (o.mn_major) {          // rows are reduction indices
+        const float s = sc[r0 + (row % rows_per_slab)];
+        x.x *= s; x.y *= s; x.z *= s; x.w *= s;
+      } else {                   // columns are reduction indices; logical 16-byte chunk = physical ^ (row & 7)
+        const int c = (idx & 7) ^ (row & 7);
+        const float4 s = *reinterpret_cast<const float4*>(sc + r0 + c * 4);
+        x.x *= s.x; x.y *= s.y; x.z *= s.z; x.w *= s.w;
+      }
+    }
+    float4 h, l;
+    split4(x, h, l);
+    *p = h;
+    *reinterpret_cast<float4*>(part0 + o.part_bytes + ((size_t)idx << 4)) = l;
+  }
+}
+
+// grid = number of CTA descriptors; dynamic smem = 1024 (barriers) + stages * stage_bytes + 1024 (alignment slack).
+template <int NJT>
+__global__ void __launch_bounds__(kThreadsU, 1)
+    umma_gemm_kernel(const UmCta* __restrict__ ctas, const UmProblem* __restrict__ probs, const UmTmaOp* __restrict__ ops,
+                     const CUtensorMap* __restrict__ maps, int stages, uint32_t stage_bytes) {
+  dz::pdl_enter();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  const UmCta cta = ctas[blockIdx.x];
+  const UmProblem& p = probs[cta.prob];
+  const int ST = stages;
+  const int nst = (int)cta.nstages;
+  const int run_stages = (int)p.run_stages;
+  const int nruns = (nst + run_stages - 1) / run_stages;
+  const bool conv_a = p.A.convert != 0, conv_b = p.B.convert != 0;
+  const bool any_conv = conv_a || conv_b;
+
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);      // [ST] TMA landed
+  uint64_t* ready = full + kStagesMax;                      // [ST] converters done (only with convert)
+  uint64_t* empty = ready + kStagesMax;                     // [ST] MMAs consumed the stage
+  uint64_t* acc_full = empty + kStagesMax;                  // [2]
+  uint64_t* acc_empty = acc_full + 2;                       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint8_t* stage_base = smem + 1024;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kTmemCols = 2 * NJT;
+
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < ST; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], kConvWarps); mbar_init(&empty[s], 1); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t a_bytes = p.A.part_bytes * p.A.nparts;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer: lane q issues op q of the stage
+    const int nops = (int)cta.ops_per_stage;
+    UmTmaOp op;
+    if (lane < nops && nst > 0) op = ops[cta.op0 + lane];
+    for (int it = 0; it < nst; ++it) {
+      const int s = it % ST;
+      const uint32_t ph = (uint32_t)(it / ST) & 1u;
+      mbar_wait(&empty[s], ph ^ 1u);
+      if (lane == 0) mbar_expect_tx(&full[s], cta.tx_bytes);
+      __syncwarp();
+      if (lane < nops) {
+        const uint32_t dst = smem_u32(stage_base + (size_t)s * stage_bytes) + op.smem_off;
+        tma_load_5d(dst, maps + op.map, &full[s], op.c[0], op.c[1], op.c[2], op.c[3], op.c[4]);
+        if (it + 1 < nst) op = ops[cta.op0 + (size_t)(it + 1) * nops + lane];
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    const uint32_t idesc = make_idesc(128, NJT, (int)p.A.mn_major, (int)p.B.mn_major);
+    const uint32_t a_lbo = p.A.mn_major ? p.A.lbo : 16u, b_lbo = p.B.mn_major ? p.B.lbo : 16u;
+    const uint32_t a_step = p.A.kstep, b_step = p.B.kstep;
+    const uint32_t a_pb = p.A.part_bytes, b_pb = p.B.part_bytes;
+    const bool a_exact = p.A.nparts == 1, b_exact = p.B.nparts == 1;
+    const int ksteps = (int)p.ksteps;
+    for (int it = 0; it < nst; ++it) {
+      const int s = it % ST;
+      const uint32_t ph = (uint32_t)(it / ST) & 1u;
+      const int run = it / run_stages, in_run = it - run * run_stages;
+      const int buf = run & 1;
+      if (in_run == 0) {
+        mbar_wait(&acc_empty[buf], (((uint32_t)run >> 1) & 1u) ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      mbar_wait(any_conv ? &ready[s] : &full[s], ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t st = smem_u32(stage_base + (size_t)s * stage_bytes);
+        const uint32_t a_hi = st, a_lo = st + a_pb, b_hi = st + a_bytes, b_lo = b_hi + b_pb;
+        const uint32_t d = tmem_base + (uint32_t)(buf * NJT);
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t dah = make_desc_sw128(a_hi + k * a_step, a_lbo, 1024), dal = make_desc_sw128(a_lo + k * a_step, a_lbo, 1024);
+          const uint64_t dbh = make_desc_sw128(b_hi + k * b_step, b_lbo, 1024), dbl = make_desc_sw128(b_lo + k * b_step, b_lbo, 1024);
+          uint32_t acc = (in_run > 0 || k > 0) ? 1u : 0u;
+          if (!a_exact) { mma_tf32(d, dal, dbh, idesc, acc); acc = 1u; }   // small cross terms first
+          if (!b_exact) { mma_tf32(d, dah, dbl, idesc, acc); acc = 1u; }
+          mma_tf32(d, dah, dbh, idesc, acc);
+        }
+        mma_commit(&empty[s]);
+        if (in_run == run_stages - 1 || it == nst - 1) mma_commit(&acc_full[buf]);
+      }
+      __syncwarp();
+    }
+  } else if (warp < 6) {
+    // ---------------------------------------------------------------- epilogue: drain runs, then write
+    const int quarter = warp & 3;
+    float sum[NJT];
+#pragma unroll
+    for (int t = 0; t < NJT; ++t) sum[t] = 0.f;
+    for (int run = 0; run < nruns; ++run) {
+      const int buf = run & 1;
+      mbar_wait(&acc_full[buf], ((uint32_t)run >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * NJT);
+#pragma unroll
+      for (int c0 = 0; c0 < NJT; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c0, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int t = 0; t < 32; ++t) sum[c0 + t] += __uint_as_float(r[t]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+    const int r = quarter * 32 + lane;
+    if (p.epi == UM_EPI_PARTIAL) {
+      const int i = cta.i0 + r;
+      if (i < p.MI) {
+        float* dst = p.C + (long long)cta.split * p.split_stride + (long long)i * p.sc_i;
+        const float s = p.scale_i ? p.scale_i[i] : 1.0f;
+        const long long sc_j = p.sc_j;
+        const int NJ = p.NJ;
+#pragma unroll
+        for (int t = 0; t < NJT; ++t)
+          if (t < NJ) dst[(long long)t * sc_j] = sum[t] * s;
+      }
+    } else {
+      const int pw = p.pw;
+      const int ro = r / pw, ri = r - ro * pw;
+      if (ro < cta.ph_valid && ri < cta.pw_valid) {
+        const long long dst = (long long)cta.row_base + (long long)ro * p.rs_outer + (long long)ri * p.rs_inner;
+        const int NJ = p.NJ;
+        const long long ld = p.out_ld;
+        const float* bias = p.bias;
+        const float* mask = p.mask ? p.mask + dst * ld : nullptr;
+        float* oh = p.out_hi ? p.out_hi + dst * ld : nullptr;
+        float* ol = p.out_lo ? p.out_lo + dst * ld : nullptr;
+        float* of = p.out_f32 ? p.out_f32 + dst * ld : nullptr;
+        const bool relu = p.relu != 0;
+#pragma unroll
+        for (int t = 0; t < NJT; t += 4) {
+          if (t < NJ) {
+            float4 v = make_float4(sum[t], sum[t + 1], sum[t + 2], sum[t + 3]);
+            if (bias) { const float4 b4 = *reinterpret_cast<const float4*>(bias + t); v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
+            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            if (mask) {
+              const float4 m4 = *reinterpret_cast<const float4*>(mask + t);
+              v.x = m4.x > 0.f ? v.x : 0.f; v.y = m4.y > 0.f ? v.y : 0.f; v.z = m4.z > 0.f ? v.z : 0.f; v.w = m4.w > 0.f ? v.w : 0.f;
+            }
+            if (of) *reinterpret_cast<float4*>(of + t) = v;
+            if (oh) {
+              float4 h, l;
+              split4(v, h, l);
+              *reinterpret_cast<float4*>(oh + t) = h;
+              *reinterpret_cast<float4*>(ol + t) = l;
+            }
+          }
+        }
+      }
+    }
+  } else if (any_conv) {
+    // ---------------------------------------------------------------- converter warps: raw fp32 -> hi / lo in place
+    const int ct = threadIdx.x - 6 * 32;
+    const UmOperand oa = p.A, ob = p.B;
+    const int red = (int)p.red_per_stage;
+    for (int it = 0; it < nst; ++it) {
+      const int s = it % ST;
+      const uint32_t ph = (uint32_t)(it / ST) & 1u;
+      mbar_wait(&full[s], ph);
+      uint8_t* st = stage_base + (size_t)s * stage_bytes;
+      const int r0 = cta.r0 + it * red;
+      if (conv_a) convert_part(oa, st, r0, ct);
+      if (conv_b) convert_part(ob, st + a_bytes, r0, ct);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ready[s]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+}  // namespace um
+}  // namespace dz

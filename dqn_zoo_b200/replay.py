@@ -718,6 +718,18 @@ class _TransitionStore:
               _stream())
     return s_tm1, a, r, d, s_t
 
+  def get_rows(self, structure, slots, chunk=4096):
+    """`[storage[i] for i in ids]` (`replay.py:153-156`): rows are gathered on the device and copied to the host in
+    chunks, so the staging memory is bounded (2 * chunk * obs_bytes) whatever the number of rows — `get_state()` of a
+    full 1M-capacity replay goes through here."""
+    out = []
+    dev = self.action.device
+    for lo in range(0, len(slots), chunk):
+      part = np.ascontiguousarray(slots[lo:lo + chunk])
+      tr = self.to_host_transition(structure, self.gather(torch.as_tensor(part, device=dev), len(part)))
+      out.extend(type(structure)(*[f[k] for f in tr]) for k in range(len(part)))
+    return out
+
   def to_host_transition(self, structure, tensors):
     s_tm1, a, r, d, s_t = [t.cpu().numpy() for t in tensors]
     shape = (len(a),) + self.obs_shape
@@ -795,9 +807,7 @@ class TransitionReplay:
     for i in ids:
       if not self._live_ids or not (self._live_ids[0] <= i <= self._live_ids[-1]):
         raise KeyError(i)
-    d_slots = torch.as_tensor(np.asarray(ids, dtype=np.int64) % self._capacity, device=self._store.action.device)
-    tr = self._store.to_host_transition(self._structure, self._store.gather(d_slots, len(ids)))
-    return [type(self._structure)(*[f[k] for f in tr]) for k in range(len(ids))]
+    return self._store.get_rows(self._structure, np.asarray(ids, dtype=np.int64) % self._capacity)
 
   def sample_device(self, size: int):
     """Host randint draw (`replay.py:78`), device id lookup + gather; returns device tensors."""
@@ -929,9 +939,7 @@ class PrioritizedTransitionReplay:
     for i in ids:
       if i not in self._distribution._id_to_index:
         raise KeyError(i)
-    d_slots = torch.as_tensor(np.asarray(ids, dtype=np.int64) % self._capacity, device=self._store.action.device)
-    tr = self._store.to_host_transition(self._structure, self._store.gather(d_slots, len(ids)))
-    return [type(self._structure)(*[f[k] for f in tr]) for k in range(len(ids))]
+    return self._store.get_rows(self._structure, np.asarray(ids, dtype=np.int64) % self._capacity)
 
   def sample_device(self, size: int):
     """Sampling + gather, everything left on the device: (ids, indices, slots, probs, weights, batch)."""

@@ -347,6 +347,14 @@ int dz_test_tc_pgemm(const float* d_A, int32_t a_rows, int32_t a_ld, int32_t a_r
                      int32_t b_rows, int32_t b_ld, int32_t b_red_contig, int32_t red, int32_t a_ones_row,
                      float* d_work, float* d_C, int64_t sc_i, int64_t sc_j, int32_t splits, int64_t split_stride,
                      const float* d_bias, int32_t relu, void* stream);
+/* Self-test of the TMA-fed tcgen05 GEMM family (csrc/dz_umma.cuh; conv / FC layers of the batch-32 step):
+ * C[MI][NJ] = sum_r A(i,r) B(j,r), NJ <= 64.  x_mn_major = 0: the operand is stored [rows][R]; 1: [R][rows] (the
+ * instruction descriptor transposes).  convert = 0: operands pre-split into tf32 hi/lo arrays (activation path);
+ * 1: raw fp32 tiles split in shared memory by the converter warps (weight path), A optionally scaled by
+ * d_scale_r[r].  epi_rows = 1: row epilogue (+ d_bias[j], relu; tf32 hi/lo copies in d_hi / d_lo).  Synchronizes. */
+int dz_test_umma_gemm(const float* d_A, int32_t a_mn_major, const float* d_B, int32_t b_mn_major, int32_t MI, int32_t NJ,
+                      int32_t R, int32_t convert, const float* d_scale_r, int32_t run_stages, int32_t epi_rows,
+                      const float* d_bias, int32_t relu, float* d_C, float* d_hi, float* d_lo, void* stream);
 
 #ifdef __cplusplus
 }

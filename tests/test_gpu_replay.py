@@ -55,3 +55,25 @@ def test_synthetic_fill_matches_oracle_rows(dev):
   np.testing.assert_array_equal(rep._store.action[torch.as_tensor(rows, device='cuda')].cpu().numpy(), a)
   np.testing.assert_array_equal(rep._store.reward[torch.as_tensor(rows, device='cuda')].cpu().numpy(), r)
   np.testing.assert_array_equal(rep._store.discount[torch.as_tensor(rows, device='cuda')].cpu().numpy(), d)
+
+
+def test_get_state_and_gather_beyond_32767_rows(dev):
+  """the gather put the row index on grid.y (<= 65535 blocks => <= 32767 rows) and `get_state()` gathered
+  every live row in one call.  40k rows now round-trip through get_state()/set_state(); the uniform sampler takes
+  batches above 1024 as the reference does (replay.py:76-82 has no limit)."""
+  cap = 40000
+  rep = dev.TransitionReplay(cap, dev.Transition(None, None, None, None, None), np.random.RandomState(2))
+  dev.bulk_fill_synthetic(rep, (4, 4, 4), 13, 6)
+  st = rep.get_state()
+  assert len(st['storage']) == cap
+  ids = np.array([i for i, _ in st['storage']])
+  obs, a, r, d = replay_oracle.synthetic_rows(13, ids, 64, 6)
+  got = np.stack([t.s_tm1 for _, t in st['storage']]).reshape(cap, -1)
+  np.testing.assert_array_equal(got, obs[:, 0])
+  np.testing.assert_array_equal(np.array([t.a_tm1 for _, t in st['storage']]), a)
+  rep2 = dev.TransitionReplay(cap, dev.Transition(None, None, None, None, None), np.random.RandomState(2))
+  rep2.set_state(st)
+  rows = rep2.get([0, 32767, 32768, cap - 1])
+  np.testing.assert_array_equal(np.stack([t.s_t for t in rows]).reshape(4, -1), obs[[0, 32767, 32768, cap - 1], 1])
+  big = rep.sample(5000)
+  assert big.s_tm1.shape == (5000, 4, 4, 4)
