@@ -20,7 +20,7 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 
 }  // namespace
 
-int UmPlan::add_map(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+int UmPlan::add_map(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, bool mn_major) {
   auto fn = encode_fn();
   if (!fn) { fail(DZ_ECUDA, "cuTensorMapEncodeTiled entry point not available"); return -1; }
   cuuint64_t gd[5] = {1, 1, 1, 1, 1};
@@ -43,7 +43,7 @@ int UmPlan::add_map(const void* base, int rank, const uint64_t* dims, const uint
   if (bx[0] * 4 > 128) { fail(DZ_EINVAL, "tensor map: inner box wider than the 128-byte swizzle span"); return -1; }
   CUtensorMap m;
   CUresult rc = fn(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) {
     char buf[256];
     snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed (%d): dims %llu %llu %llu %llu %llu strides %llu %llu %llu %llu box %u %u %u %u %u", (int)rc,
@@ -156,7 +156,7 @@ extern "C" int dz_test_umma_gemm(const float* d_A, int32_t a_mn_major, const flo
       uint32_t box[2];
       if (!mn_major) { dims[0] = (uint64_t)R; dims[1] = (uint64_t)rows; strides[0] = (uint64_t)R * 4; box[0] = 32; box[1] = (uint32_t)tile_rows; }
       else { dims[0] = (uint64_t)rows; dims[1] = (uint64_t)R; strides[0] = (uint64_t)rows * 4; box[0] = 32; box[1] = 32; }
-      out[part] = plan.add_map(src[part], 2, dims, strides, box);
+      out[part] = plan.add_map(src[part], 2, dims, strides, box, mn_major != 0);
       if (out[part] < 0) return DZ_EINVAL;
     }
     return DZ_OK;

@@ -111,14 +111,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
 
 // 64-bit shared-memory matrix descriptor, SWIZZLE_128B canonical layouts (cute/arch/mma_sm100_desc.hpp):
 //   K-major : rows of 128 B, 8-row groups SBO = 1024 B apart, LBO unused
-//   MN-major: [8 r rows][128 B of mn] atoms; LBO = bytes between atoms along MN, SBO = bytes between 8-row groups along r
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   MN-major: 32-bit operands can only be transposed from the "128B swizzle, 32B atom" layout (SWIZZLE_128B_BASE32B;
+//             measured: plain SWIZZLE_128B / no-swizzle MN-major tf32 descriptors make the MMA return zeros, and CUTLASS
+//             sm100_common.inl says the same): [4 r rows][128 B of mn] atoms, 32-byte chunks XOR-ed with (row & 3) —
+//             the TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  LBO = bytes between atoms along MN, SBO = 512.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;   // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;   // layout type SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;   // 2: SWIZZLE_128B, 1: SWIZZLE_128B_BASE32B
   return d;
 }
 
@@ -234,6 +237,8 @@ __global__ void __launch_bounds__(kThreadsU, 1)
     // ---------------------------------------------------------------- MMA issuer
     const uint32_t idesc = make_idesc(128, NJT, (int)p.A.mn_major, (int)p.B.mn_major);
     const uint32_t a_lbo = p.A.mn_major ? p.A.lbo : 16u, b_lbo = p.B.mn_major ? p.B.lbo : 16u;
+    const uint32_t a_sbo = p.A.mn_major ? 512u : 1024u, b_sbo = p.B.mn_major ? 512u : 1024u;
+    const uint32_t a_lt = p.A.mn_major ? 1u : 2u, b_lt = p.B.mn_major ? 1u : 2u;
     const uint32_t a_step = p.A.kstep, b_step = p.B.kstep;
     const uint32_t a_pb = p.A.part_bytes, b_pb = p.B.part_bytes;
     const bool a_exact = p.A.nparts == 1, b_exact = p.B.nparts == 1;
@@ -254,8 +259,8 @@ __global__ void __launch_bounds__(kThreadsU, 1)
         const uint32_t a_hi = st, a_lo = st + a_pb, b_hi = st + a_bytes, b_lo = b_hi + b_pb;
         const uint32_t d = tmem_base + (uint32_t)(buf * NJT);
         for (int k = 0; k < ksteps; ++k) {
-          const uint64_t dah = make_desc_sw128(a_hi + k * a_step, a_lbo, 1024), dal = make_desc_sw128(a_lo + k * a_step, a_lbo, 1024);
-          const uint64_t dbh = make_desc_sw128(b_hi + k * b_step, b_lbo, 1024), dbl = make_desc_sw128(b_lo + k * b_step, b_lbo, 1024);
+          const uint64_t dah = make_desc_sw128(a_hi + k * a_step, a_lbo, a_sbo, a_lt), dal = make_desc_sw128(a_lo + k * a_step, a_lbo, a_sbo, a_lt);
+          const uint64_t dbh = make_desc_sw128(b_hi + k * b_step, b_lbo, b_sbo, b_lt), dbl = make_desc_sw128(b_lo + k * b_step, b_lbo, b_sbo, b_lt);
           uint32_t acc = (in_run > 0 || k > 0) ? 1u : 0u;
           if (!a_exact) { mma_tf32(d, dal, dbh, idesc, acc); acc = 1u; }   // small cross terms first
           if (!b_exact) { mma_tf32(d, dah, dbl, idesc, acc); acc = 1u; }

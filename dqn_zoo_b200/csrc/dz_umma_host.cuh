@@ -28,8 +28,9 @@ struct UmPlan {
   UmTmaOp* d_ops = nullptr;
 
   // 5-D fp32 tensor map with SWIZZLE_128B; dims/strides innermost first (strides in BYTES for dims 1..4; dims beyond
-  // `rank` are 1).  Returns the map index or -1 (error string set).
-  int add_map(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+  // `rank` are 1).  mn_major: the tile feeds an MN-major (transposing) descriptor -> 32-byte-atom flavour of the swizzle.
+  // Returns the map index or -1 (error string set).
+  int add_map(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, bool mn_major = false);
   int upload();          // (re)allocates and copies all four tables
   void release();
   int launch(const char* tag, const UmLaunch& l, void* stream) const;

@@ -718,7 +718,7 @@ int build_plan(UmNet* n) {
           const float* w = (blob ? d.target : d.online) + (sg ? d.off_fc_sw[s] : d.off_fc_w[s]);
           uint64_t dims[2] = {512, (uint64_t)feat}, strides[1] = {2048};
           uint32_t box[2] = {32, 32};
-          m_wf_fc[blob][s][sg] = pl.add_map(w, 2, dims, strides, box);
+          m_wf_fc[blob][s][sg] = pl.add_map(w, 2, dims, strides, box, true);   // MN-major A operand (rows of W are the reduction)
           if (m_wf_fc[blob][s][sg] < 0) return DZ_EINVAL;
           if (blob == 0) {
             uint32_t boxd[2] = {32, 128};
