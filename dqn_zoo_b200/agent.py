@@ -106,6 +106,11 @@ class _DeviceAgent(parts.Agent):
       self._learn()
     if self._frame_t % self._target_network_update_period == 0:
       self._learner.sync_target()
+      # The fused step only RECORDS bad priorities / non-finite weights as sticky device flags (no per-step D2H sync);
+      # read them on the target-update cadence so a diverged run stops with the reference's exceptions
+      # (replay.py:281-282 'value must be finite and positive', :240-241 'Weights are not finite') instead of
+      # training on with stale priorities.
+      self.check_device_flags()
     return action
 
   def reset(self) -> None:
@@ -214,7 +219,11 @@ class _DeviceAgent(parts.Agent):
     host = slot.numpy()
     host[:B].view(np.int64)[:] = rs.randint(size, size=B)
     if self.PRIORITIZED:
-      host[B:2 * B] = rs.uniform(size=B)     # scaled by the root on the device; root == 0 raises a flag
+      # Scaled by the root on the device.  KNOWN DIVERGENCE: the reference skips this draw when the root is 0
+      # (replay.py:556-560); the root lives on the device here and is not read back per step, so the draw is always
+      # consumed and the kernel raises DZ_FLAG_ROOT_ZERO instead (surfaced by check_device_flags on the target-update
+      # cadence).  A zero root needs every stored priority to be 0, which the agents' priority rule never produces.
+      host[B:2 * B] = rs.uniform(size=B)
       host[2 * B:3 * B] = rs.uniform(size=B)
       dist = self._replay._distribution
       host[3 * B:] = (float(size), float(self._replay.importance_sampling_exponent),
@@ -291,7 +300,11 @@ class _DeviceAgent(parts.Agent):
     f = int(flags.item())
     if f:
       flags.zero_()
-      raise RuntimeError('device error flags: %d' % f)
+      if f & (_lib.DZ_FLAG_BAD_VALUE | _lib.DZ_FLAG_BAD_INDEX):
+        raise ValueError('value must be finite and positive, index in range (device flags %d).' % f)
+      if f & _lib.DZ_FLAG_NONFINITE_WEIGHT:
+        raise ValueError('Weights are not finite (device flags %d).' % f)
+      raise RuntimeError('device error flags: %d (bad sum-tree target / empty tree in the fused sampler)' % f)
 
 
 class Dqn(_DeviceAgent):

@@ -2,7 +2,9 @@
 
 Same class names, constructor arguments, return types/dtypes and exceptions as the
 reference (cited per method), so agents and tests written for `dqn_zoo.replay`
-run unchanged.  What differs is where things live:
+run unchanged, with two stated differences: a (snappy) encoder/decoder pair is applied as a
+host round trip at insert time instead of at rest, and the accumulators return lists, not
+generators.  What else differs is where things live:
 
   * transition storage (`OrderedDict` in the reference, `replay.py:140,688`) is a
     transition-major uint8 array in device memory: row = id % capacity holds
@@ -755,9 +757,15 @@ def _host_obs(x, store):
 
 
 def _check_codec(encoder, decoder):
-  if encoder is not None or decoder is not None:
-    raise NotImplementedError('encoder/decoder (snappy compress_state, replay.py:895-904) are not used: HBM holds '
-                              'raw uint8 observations; pass None.')
+  """The reference stores `encoder(item)` and returns `decoder(stored)` (`replay.py:148,155`; every run_atari.py passes
+  the snappy pair of `replay.py:895-904` so that 1M x 56 KB fits in host RAM).  HBM holds raw observations, so a codec
+  pair is accepted and applied as the round trip `decoder(encoder(item))` on the host at insert time — the identity
+  for a lossless codec such as snappy — and both must be given together."""
+  if (encoder is None) != (decoder is None):
+    raise ValueError('encoder and decoder must be given together')
+  if encoder is None:
+    return None
+  return lambda item: decoder(encoder(item))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -769,7 +777,7 @@ class TransitionReplay:
   """Uniform replay with oldest-out eviction (`replay.py:120-200`), storage in HBM."""
 
   def __init__(self, capacity: int, structure, random_state: np.random.RandomState, encoder=None, decoder=None):
-    _check_codec(encoder, decoder)
+    self._codec = _check_codec(encoder, decoder)
     self._capacity = capacity
     self._structure = structure
     self._random_state = random_state
@@ -786,6 +794,8 @@ class TransitionReplay:
 
   def add(self, item) -> None:
     """`replay.py:142-151`."""
+    if self._codec is not None:
+      item = self._codec(item)
     s_tm1 = _host_obs(item[0], self._store)
     s_t = _host_obs(item[4], self._store)
     if self.size == self._capacity:
@@ -882,7 +892,7 @@ class PrioritizedTransitionReplay:
   def __init__(self, capacity: int, structure, priority_exponent: float,
                importance_sampling_exponent: Callable[[int], float], uniform_sample_probability: float,
                normalize_weights: bool, random_state: np.random.RandomState, encoder=None, decoder=None):
-    _check_codec(encoder, decoder)
+    self._codec = _check_codec(encoder, decoder)
     self._capacity = capacity
     self._structure = structure
     self._random_state = random_state
@@ -905,6 +915,8 @@ class PrioritizedTransitionReplay:
     """`replay.py:690-699`: one device call carries the row, the list patches, the evicted
     leaf's zeroing and the new leaf (= priority**alpha evaluated in float64 on the host, as
     `replay.py:507` does)."""
+    if self._codec is not None:
+      item = self._codec(item)
     s_tm1 = _host_obs(item[0], self._store)
     s_t = _host_obs(item[4], self._store)
     dist = self._distribution

@@ -172,3 +172,16 @@ def test_bilinear_axis_tables_match_oracle():
     ob, ok, oks = po.resample_coeffs(in_size, out_size)
     assert ks == oks and np.array_equal(b, ob) and np.array_equal(k, ok)
   assert processors.LUMA == po.LUMA
+
+
+def test_codec_pair_is_validated_on_the_host():
+  """replay.py:148,155: the reference stores encoder(item) and hands out decoder(stored).  The device replay takes the
+  pair and applies the round trip at insert; giving only one of the two is an error (checked before any CUDA call)."""
+  from dqn_zoo_b200 import replay
+  assert replay._check_codec(None, None) is None
+  rt = replay._check_codec(lambda t: t._replace(r_t=t.r_t * 2), lambda t: t._replace(r_t=t.r_t / 2))
+  item = replay.Transition(s_tm1=1, a_tm1=2, r_t=3.0, discount_t=0.5, s_t=4)
+  assert rt(item) == item
+  import pytest
+  with pytest.raises(ValueError):
+    replay._check_codec(lambda t: t, None)
