@@ -2410,11 +2410,21 @@ int dz_learner_sync_target(dz_learner* l, void* stream) {
   return DZ_OK;
 }
 
+// Test hook: device-to-device copy out of an internal buffer (tests hold only the raw pointer).
+int dz_test_copy(void* d_dst, const void* d_src, int64_t bytes, void* stream) {
+  DZ_CUDA_OK(cudaMemcpyAsync(d_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return DZ_OK;
+}
+
 // Test hook: device pointer + element count of an internal activation / gradient buffer (tests and tools only).
 int dz_test_learner_buffer(dz_learner* l, const char* name, float** d_ptr, int64_t* count) {
   const std::string n = name;
   const int64_t rows0 = (int64_t)l->B * l->n_head[0];
   if (n == "act3") { *d_ptr = l->act3[0]; *count = (int64_t)l->B * l->d.feat; }
+  else if (n == "act1") { *d_ptr = l->act1[0]; *count = (int64_t)l->B * l->d.h1 * l->d.w1 * 32; }
+  else if (n == "act2") { *d_ptr = l->act2[0]; *count = (int64_t)l->B * l->d.h2 * l->d.w2 * 64; }
+  else if (n == "h1_val") { *d_ptr = l->h1[0][1]; *count = l->h1[0][1] ? rows0 * 512 : 0; }
+  else if (n == "iqn_e0") { *d_ptr = l->E0; *count = l->E0 ? rows0 * l->d.feat : 0; }
   else if (n == "h1") { *d_ptr = l->h1[0][0]; *count = rows0 * 512; }
   else if (n == "dh1") { *d_ptr = l->dh1[0]; *count = rows0 * 512; }
   else if (n == "iqn_hi") {

@@ -339,9 +339,11 @@ int dz_jax_uniform(const uint32_t* d_keys, const int64_t* counts, int32_t nblock
 /* threefry2x32 (20 rounds) evaluated on the HOST by the same source the kernel compiles; tests only. */
 int dz_test_threefry2x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t* out2);
 
-/* Device pointer + element count of an internal learner buffer ("act3", "h1", "dh1", "iqn_hi", "iqn_dhi");
+/* Device pointer + element count of an internal learner buffer of the last update (pass 0: "act1", "act2", "act3",
+ * "h1", "h1_val", "dh1", "iqn_e0", "iqn_hi", "iqn_dhi");
  * tests/tools only. */
 int dz_test_learner_buffer(dz_learner* l, const char* name, float** d_ptr, int64_t* count);
+int dz_test_copy(void* d_dst, const void* d_src, int64_t bytes, void* stream);   /* device-to-device, tests only */
 int64_t dz_test_tc_pgemm_work(int32_t a_rows, int32_t b_rows, int32_t red);
 int dz_test_tc_pgemm(const float* d_A, int32_t a_rows, int32_t a_ld, int32_t a_red_contig, const float* d_B,
                      int32_t b_rows, int32_t b_ld, int32_t b_red_contig, int32_t red, int32_t a_ones_row,

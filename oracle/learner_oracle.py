@@ -149,12 +149,34 @@ def _conv(x, w, b, stride):
   return y.permute(0, 2, 3, 1)
 
 
-def torso(p, obs_u8, dtype):
+class ReluTap:
+  """Test instrumentation for the ReLU kinks of ONE network apply.  `pre[name]` records every pre-activation; if
+  `masks[name]` (bool, same shape) is given, relu(x) is replaced by x * mask, i.e. the gradient is evaluated on the
+  given activation pattern.  The GPU tests use it to separate two things the 1e-5 gradient bar mixes up: arithmetic
+  error, and units whose float64 pre-activation is within float32 rounding of zero and therefore legitimately fall
+  on the other side of the kink in ANY float32 evaluation (each flips one 0/1 factor of the gradient)."""
+
+  def __init__(self, masks=None):
+    self.pre = {}
+    self.masks = masks or {}
+
+  def relu(self, x, name):
+    self.pre[name] = x.detach()
+    if name in self.masks:
+      return x * self.masks[name].to(x.dtype).reshape(x.shape)
+    return F.relu(x)
+
+
+def _relu(x, tap, name):
+  return F.relu(x) if tap is None else tap.relu(x, name)
+
+
+def torso(p, obs_u8, dtype, tap=None):
   """`networks.py:181-204`: /255, three conv+relu, flatten in (H,W,C) order."""
   x = obs_u8.to(dtype) / 255.0
-  x = F.relu(_conv(x, p['conv1/w'], p['conv1/b'], 4))
-  x = F.relu(_conv(x, p['conv2/w'], p['conv2/b'], 2))
-  x = F.relu(_conv(x, p['conv3/w'], p['conv3/b'], 1))
+  x = _relu(_conv(x, p['conv1/w'], p['conv1/b'], 4), tap, 'conv1')
+  x = _relu(_conv(x, p['conv2/w'], p['conv2/b'], 2), tap, 'conv2')
+  x = _relu(_conv(x, p['conv3/w'], p['conv3/b'], 1), tap, 'conv3')
   return x.reshape(x.shape[0], -1)
 
 
@@ -167,18 +189,18 @@ def _noisy(p, prefix, x, eps_in, eps_out, with_bias):
   return mu + sig * eps_out
 
 
-def apply_net(spec, p, obs_u8, dtype, taus=None, noise=None):
+def apply_net(spec, p, obs_u8, dtype, taus=None, noise=None, tap=None):
   """One `network.apply`.  Returns dict with the NamedTuple fields of
-  `networks.py:34-55` for the family."""
-  feat = torso(p, obs_u8, dtype)
+  `networks.py:34-55` for the family.  `tap`: optional ReluTap (tests)."""
+  feat = torso(p, obs_u8, dtype, tap)
   kind = spec.kind
   a = spec.num_actions
   if kind == 'rainbow':
     k = spec.num_atoms
     n = {name: noise[name].to(dtype)[None, :] for name, _ in noise_shapes(spec)}
-    adv = F.relu(_noisy(p, 'adv1', feat, n['adv1/in'], n['adv1/out'], True))
+    adv = _relu(_noisy(p, 'adv1', feat, n['adv1/in'], n['adv1/out'], True), tap, 'adv1')
     adv = _noisy(p, 'adv2', adv, n['adv2/in'], n['adv2/out'], False).reshape(-1, a, k)
-    val = F.relu(_noisy(p, 'val1', feat, n['val1/in'], n['val1/out'], True))
+    val = _relu(_noisy(p, 'val1', feat, n['val1/in'], n['val1/out'], True), tap, 'val1')
     val = _noisy(p, 'val2', val, n['val2/in'], n['val2/out'], False).reshape(-1, 1, k)
     logits = val + adv - adv.mean(dim=1, keepdim=True)          # `networks.py:251`
     support = support_atoms(spec, dtype)
@@ -192,12 +214,12 @@ def apply_net(spec, p, obs_u8, dtype, taus=None, noise=None):
     pi_mult = torch.arange(1, latent + 1, dtype=torch.float32) * float(np.float32(np.pi))
     arg = (pi_mult[None, None, :] * taus.to(torch.float32)[:, :, None]).to(dtype)
     emb = torch.cos(arg)                                                     # [B,N,latent]
-    emb = F.relu(emb @ p['embed/w'] + p['embed/b'])                          # [B,N,D]
+    emb = _relu(emb @ p['embed/w'] + p['embed/b'], tap, 'embed')              # [B,N,D]
     h = emb * feat[:, None, :]
-    h = F.relu(h @ p['fc1/w'] + p['fc1/b'])
+    h = _relu(h @ p['fc1/w'] + p['fc1/b'], tap, 'fc1')
     q_dist = h @ p['head/w'] + p['head/b']                                   # [B,N,A]
     return {'q_dist': q_dist, 'q_values': q_dist.mean(dim=1).detach()}
-  h = F.relu(feat @ p['fc1/w'] + p['fc1/b'])
+  h = _relu(feat @ p['fc1/w'] + p['fc1/b'], tap, 'fc1')
   out = h @ p['head/w'] + p['head/b']          # shared bias (1,) broadcasts (`networks.py:130-132`)
   if kind in ('dqn', 'double_q', 'prioritized'):
     return {'q_values': out}
@@ -269,7 +291,7 @@ def quantile_regression_loss(dist_src, tau_src, dist_target, kappa):
 
 
 def loss_fn(spec, online, target, batch, dtype, weights=None, taus=None, noise=None,
-            grad_error_bound=1.0 / 32, huber_param=1.0):
+            grad_error_bound=1.0 / 32, huber_param=1.0, tap=None):
   """Returns (scalar loss, aux dict).  `batch` = dict(s_tm1,a_tm1,r_t,discount_t,s_t) of
   torch tensors; r_t/discount_t are cast to `dtype` AFTER a float32 rounding, as the
   reference feeds float32 into jit.  Cites: dqn `dqn/agent.py:85-107`, double_q
@@ -284,7 +306,7 @@ def loss_fn(spec, online, target, batch, dtype, weights=None, taus=None, noise=N
   rows = torch.arange(s_tm1.shape[0])
   aux = {}
   if kind in ('dqn', 'double_q', 'prioritized'):
-    q_tm1 = apply_net(spec, online, s_tm1, dtype)['q_values']
+    q_tm1 = apply_net(spec, online, s_tm1, dtype, tap=tap)['q_values']
     q_target = apply_net(spec, target, s_t, dtype)['q_values'].detach()
     if kind == 'dqn':
       boot = q_target.max(dim=1).values
@@ -301,11 +323,11 @@ def loss_fn(spec, online, target, batch, dtype, weights=None, taus=None, noise=N
     support = support_atoms(spec, dtype)
     nz = noise or [None, None, None]
     if kind == 'rainbow':
-      out_tm1 = apply_net(spec, online, s_tm1, dtype, noise=nz[0])
+      out_tm1 = apply_net(spec, online, s_tm1, dtype, noise=nz[0], tap=tap)
       sel_q = apply_net(spec, online, s_t, dtype, noise=nz[1])['q_values'].detach()
       tgt = apply_net(spec, target, s_t, dtype, noise=nz[2])
     else:
-      out_tm1 = apply_net(spec, online, s_tm1, dtype)
+      out_tm1 = apply_net(spec, online, s_tm1, dtype, tap=tap)
       tgt = apply_net(spec, target, s_t, dtype)
       sel_q = tgt['q_values'].detach()
     a_star = sel_q.argmax(dim=1)
@@ -319,7 +341,7 @@ def loss_fn(spec, online, target, batch, dtype, weights=None, taus=None, noise=N
   elif kind == 'qrdqn':
     n = spec.num_quantiles
     quantiles = ((torch.arange(0, n, dtype=torch.float32) + 0.5) / float(n)).to(dtype)   # `qrdqn/run_atari.py:136-137`
-    dist_tm1 = apply_net(spec, online, s_tm1, dtype)['q_dist']
+    dist_tm1 = apply_net(spec, online, s_tm1, dtype, tap=tap)['q_dist']
     dist_t = apply_net(spec, target, s_t, dtype)['q_dist'].detach()
     a_star = dist_t.mean(dim=1).argmax(dim=1)
     tgt = (r[:, None] + disc[:, None] * dist_t[rows, :, a_star]).detach()
@@ -327,7 +349,7 @@ def loss_fn(spec, online, target, batch, dtype, weights=None, taus=None, noise=N
     aux['dist_tm1'] = dist_tm1.detach()
   elif kind == 'iqn':
     tau_tm1, tau_sel, tau_t = taus
-    dist_tm1 = apply_net(spec, online, s_tm1, dtype, taus=tau_tm1)['q_dist']
+    dist_tm1 = apply_net(spec, online, s_tm1, dtype, taus=tau_tm1, tap=tap)['q_dist']
     dist_sel = apply_net(spec, target, s_t, dtype, taus=tau_sel)['q_dist'].detach()
     dist_t = apply_net(spec, target, s_t, dtype, taus=tau_t)['q_dist'].detach()
     a_star = dist_sel.mean(dim=1).argmax(dim=1)
@@ -425,9 +447,9 @@ class Learner:
     self.target = {k: v.clone() for k, v in self.online.items()}
     self.state = init_opt_state(self.opt, self.online)
 
-  def grads(self, batch, weights=None, taus=None, noise=None):
+  def grads(self, batch, weights=None, taus=None, noise=None, tap=None):
     p = {k: v.clone().requires_grad_(True) for k, v in self.online.items()}
-    loss, aux = loss_fn(self.spec, p, self.target, batch, self.dtype, weights, taus, noise)
+    loss, aux = loss_fn(self.spec, p, self.target, batch, self.dtype, weights, taus, noise, tap=tap)
     loss.backward()
     g = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in p.items()}
     return loss.detach(), aux, g
