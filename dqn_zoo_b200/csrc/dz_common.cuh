@@ -49,10 +49,22 @@ __device__ __forceinline__ void pdl_enter() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 extern int g_pdl;   // -1 = read DZ_NO_PDL on first use
+extern int g_carveout;   // -1 = read DZ_CARVEOUT on first use; > 0: preferred shared-memory carveout (percent) for EVERY kernel
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   if (g_pdl < 0) { const char* e = getenv("DZ_NO_PDL"); g_pdl = (e && e[0] && e[0] != '0') ? 0 : 1; }
+  if (g_carveout < 0) { const char* e = getenv("DZ_CARVEOUT"); g_carveout = e ? atoi(e) : 0; }
+  if (g_carveout > 0) {   // experiment: one L1/shared split for the whole step, so consecutive kernels never reconfigure the SMs
+    static const void* done[64];
+    static int ndone = 0;
+    bool seen = false;
+    for (int i = 0; i < ndone; ++i) seen = seen || done[i] == (const void*)kernel;
+    if (!seen && ndone < 64) {
+      cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributePreferredSharedMemoryCarveout, g_carveout);
+      done[ndone++] = (const void*)kernel;
+    }
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute attr[1];

@@ -1818,7 +1818,9 @@ int backward_torso(dz_learner* l, const uint8_t* const* rows0, void* stream) {
   GemmBatch gb;
   if (l->um && l->cfg.kind == DZ_IQN) DZ_TRY(um_split_dact3(l->um, stream));   // dact3 came from the Hadamard kernel (fp32)
   // conv3 wgrad
-  {
+  if (l->um) {
+    DZ_TRY(um_wgrad_conv3(l->um, fork_side(l, stream)));
+  } else {
     GemmProblem p = zero_problem();
     set_conv(p, A_CONV_F32, l->act2[0], B, d.h2, d.w2, 64, 3, 3, 1);
     p.B = l->dact3; p.N = 64; p.ldb = 64; p.ldc = 64;
@@ -1843,7 +1845,9 @@ int backward_torso(dz_learner* l, const uint8_t* const* rows0, void* stream) {
               d.h3, d.w3);
   }
   // conv2 wgrad
-  {
+  if (l->um) {
+    DZ_TRY(um_wgrad_conv2(l->um, fork_side(l, stream)));
+  } else {
     GemmProblem p = zero_problem();
     set_conv(p, A_CONV_F32, l->act1[0], B, d.h1, d.w1, 32, 4, 4, 2);
     p.B = l->dact2; p.N = 64; p.ldb = 64; p.ldc = 64;
@@ -1868,7 +1872,13 @@ int backward_torso(dz_learner* l, const uint8_t* const* rows0, void* stream) {
               d.h2, d.w2);
   }
   // conv1 wgrad (A = uint8 rows in place)
-  {
+  if (l->um) {
+    void* ws = fork_side(l, stream);
+    DZ_TRY(um_wgrad_conv1(l->um, rows0, ws));
+    DZ_TRY(um_wgrad_finish(l->um, G + L.off("conv3/w"), G + L.off("conv3/b"), G + L.off("conv2/w"), G + L.off("conv2/b"),
+                           nullptr, 0, G + L.off("conv1/w"), G + L.off("conv1/b"), ws));
+    return join_side(l, stream);
+  } else {
     GemmProblem p = zero_problem();
     set_conv(p, A_CONV_U8, rows0, B, d.H, d.W, d.C, 8, 8, 4);
     p.B = l->dact1; p.N = 32; p.ldb = 32; p.ldc = 32;
@@ -1879,8 +1889,8 @@ int backward_torso(dz_learner* l, const uint8_t* const* rows0, void* stream) {
     DZ_TRY(run_tn("conv1_wgrad", gb, fork_side(l, stream)));
     fb.f[fb.n++] = FinishTN{p.C, splits, p.split_stride, p.K, 32, G + L.off("conv1/w"), nullptr, p.Cb, nullptr, nullptr, nullptr};
   }
-  dim3 grid((unsigned)ceil_div(577 * 64, 256), fb.n);
   void* ws = l->side && l->side_dirty ? (void*)l->side : stream;   // after conv1_wgrad on the same (side) stream
+  dim3 grid((unsigned)ceil_div(577 * 64, 256), fb.n);
   DZ_LAUNCH(finish_tn_kernel, grid, 256, 0, ws, fb);
   return join_side(l, stream);
 }

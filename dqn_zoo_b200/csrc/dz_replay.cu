@@ -13,6 +13,7 @@ namespace dz {
 thread_local std::string g_last_error;
 std::atomic<int64_t> g_launches{0};
 int g_pdl = -1;
+int g_carveout = -1;
 bool g_profile = false;
 
 namespace {

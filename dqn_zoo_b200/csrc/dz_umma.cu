@@ -56,6 +56,26 @@ int UmPlan::add_map(const void* base, int rank, const uint64_t* dims, const uint
   return (int)maps.size() - 1;
 }
 
+int UmPlan::localize_maps(UmLaunch& l) {
+  l.nmaps = 0;
+  for (int ci = l.cta0; ci < l.cta0 + l.nctas; ++ci) {
+    const UmCta& c = ctas[ci];
+    const size_t n = (size_t)c.nstages * c.ops_per_stage;
+    for (size_t oi = c.op0; oi < c.op0 + n; ++oi) {
+      const int id = (int)ops[oi].map;
+      int slot = -1;
+      for (int q = 0; q < l.nmaps; ++q) if (l.map_ids[q] == id) slot = q;
+      if (slot < 0) {
+        if (l.nmaps >= um::kMaxMapsPerLaunch) return fail(DZ_EINVAL, "too many tensor maps in one launch");
+        slot = l.nmaps;
+        l.map_ids[l.nmaps++] = id;
+      }
+      ops[oi].map = (uint32_t)slot;
+    }
+  }
+  return DZ_OK;
+}
+
 void UmPlan::release() {
   if (d_maps) cudaFree(d_maps);
   if (d_probs) cudaFree(d_probs);
@@ -93,16 +113,19 @@ int UmPlan::launch(const char* tag, const UmLaunch& l, void* stream) const {
   if (l.nctas <= 0) return DZ_OK;
   if (!d_ctas) return fail(DZ_EINVAL, "umma plan not uploaded");
   if (l.stages < 1 || l.stages > um::kStagesMax || l.stage_bytes % 1024) return fail(DZ_EINVAL, "umma launch geometry");
-  const size_t smem = 2048 + (size_t)l.stages * l.stage_bytes;
+  const size_t smem = 1024 + um::kCtlBytes + (size_t)l.stages * l.stage_bytes;
   if (smem > 227 * 1024) return fail(DZ_EINVAL, "umma launch needs too much shared memory");
   const int v = l.njt == 32 ? 0 : 1;
   if (l.njt != 32 && l.njt != 64) return fail(DZ_EINVAL, "umma launch: NJT must be 32 or 64");
   DZ_TRY_CFG(configure());
+  um::UmMaps lm;
+  for (int q = 0; q < l.nmaps; ++q) lm.m[q] = maps[l.map_ids[q]];
+  for (int q = l.nmaps; q < um::kMaxMapsPerLaunch; ++q) lm.m[q] = maps[l.map_ids[0]];
   if (v == 0)
-    DZ_LAUNCH_NAMED(tag, um::umma_gemm_kernel<32>, (unsigned)l.nctas, um::kThreadsU, smem, stream, d_ctas + l.cta0, d_probs, d_ops, d_maps, l.stages,
+    DZ_LAUNCH_NAMED(tag, um::umma_gemm_kernel<32>, (unsigned)l.nctas, um::kThreadsU, smem, stream, lm, d_ctas + l.cta0, d_probs, d_ops, l.nmaps, l.stages,
                     l.stage_bytes);
   else
-    DZ_LAUNCH_NAMED(tag, um::umma_gemm_kernel<64>, (unsigned)l.nctas, um::kThreadsU, smem, stream, d_ctas + l.cta0, d_probs, d_ops, d_maps, l.stages,
+    DZ_LAUNCH_NAMED(tag, um::umma_gemm_kernel<64>, (unsigned)l.nctas, um::kThreadsU, smem, stream, lm, d_ctas + l.cta0, d_probs, d_ops, l.nmaps, l.stages,
                     l.stage_bytes);
   return DZ_OK;
 }
@@ -212,10 +235,12 @@ extern "C" int dz_test_umma_gemm(const float* d_A, int32_t a_mn_major, const flo
     c.ops_per_stage = (uint32_t)nops; c.tx_bytes = tx;
     plan.ctas.push_back(c);
   }
-  rc = plan.upload();
-  if (rc != DZ_OK) return rc;
   UmLaunch l;
-  l.cta0 = 0; l.nctas = tiles; l.njt = njt; l.stage_bytes = a_bytes + b_bytes; l.stages = 4; l.convert = convert != 0;
+  l.cta0 = 0; l.nctas = tiles;
+  rc = plan.localize_maps(l);
+  if (rc == DZ_OK) rc = plan.upload();
+  if (rc != DZ_OK) return rc;
+  l.njt = njt; l.stage_bytes = a_bytes + b_bytes; l.stages = 4; l.convert = convert != 0;   // 4 x <= 48 KB + control block fits
   rc = plan.launch("umma_selftest", l, stream);
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
   plan.release();

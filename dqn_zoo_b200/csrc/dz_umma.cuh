@@ -169,23 +169,26 @@ __device__ __forceinline__ void convert_part(const UmOperand& o, uint8_t* part0,
   }
 }
 
-// grid = number of CTA descriptors; dynamic smem = 1024 (barriers) + stages * stage_bytes + 1024 (alignment slack).
+constexpr int kMaxMapsPerLaunch = 12;
+struct UmMaps { CUtensorMap m[kMaxMapsPerLaunch]; };   // passed as a __grid_constant__ kernel parameter: the TMA unit's
+                                                        // descriptor cache is fed from the constant bank (descriptors left in
+                                                        // plain global memory cost a dependent fetch per TMA operation)
+constexpr int kMaxOpsPerCta = 256;     // TMA ops of one CTA staged in shared memory (8 KB)
+constexpr int kCtlBytes = 1024 + 1024 + kMaxOpsPerCta * 32;   // barriers | problem copy | op table
+
+// grid = number of CTA descriptors; dynamic smem = kCtlBytes + stages * stage_bytes + 1024 (alignment slack).
 template <int NJT>
 __global__ void __launch_bounds__(kThreadsU, 1)
-    umma_gemm_kernel(const UmCta* __restrict__ ctas, const UmProblem* __restrict__ probs, const UmTmaOp* __restrict__ ops,
-                     const CUtensorMap* __restrict__ maps, int stages, uint32_t stage_bytes) {
+    umma_gemm_kernel(const __grid_constant__ UmMaps maps, const UmCta* __restrict__ ctas, const UmProblem* __restrict__ probs,
+                     const UmTmaOp* __restrict__ ops, int nmaps, int stages, uint32_t stage_bytes) {
+  if (threadIdx.x < nmaps) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.m[threadIdx.x])) : "memory");
   dz::pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   const UmCta cta = ctas[blockIdx.x];
-  const UmProblem& p = probs[cta.prob];
   const int ST = stages;
   const int nst = (int)cta.nstages;
-  const int run_stages = (int)p.run_stages;
-  const int nruns = (nst + run_stages - 1) / run_stages;
-  const bool conv_a = p.A.convert != 0, conv_b = p.B.convert != 0;
-  const bool any_conv = conv_a || conv_b;
 
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);      // [ST] TMA landed
   uint64_t* ready = full + kStagesMax;                      // [ST] converters done (only with convert)
@@ -193,11 +196,26 @@ __global__ void __launch_bounds__(kThreadsU, 1)
   uint64_t* acc_full = empty + kStagesMax;                  // [2]
   uint64_t* acc_empty = acc_full + 2;                       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  uint8_t* stage_base = smem + 1024;
+  UmProblem* p_smem = reinterpret_cast<UmProblem*>(smem + 1024);
+  UmTmaOp* ops_smem = reinterpret_cast<UmTmaOp*>(smem + 2048);
+  uint8_t* stage_base = smem + kCtlBytes;
+  static_assert(sizeof(UmProblem) <= 1024 && sizeof(UmProblem) % 16 == 0, "problem copy does not fit its slot");
+  static_assert(kCtlBytes % 1024 == 0, "stage base must stay 1024-byte aligned");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kTmemCols = 2 * NJT;
 
+  // The CTA's problem and its whole TMA program go to shared memory once (coalesced): the producer's per-stage
+  // work is then a shared-memory read, not a dependent global load per stage.
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(probs + cta.prob);
+    uint4* dst = reinterpret_cast<uint4*>(p_smem);
+    for (int i = threadIdx.x; i < (int)(sizeof(UmProblem) / 16); i += kThreadsU) dst[i] = src[i];
+    const int nvec = min(nst * (int)cta.ops_per_stage, kMaxOpsPerCta) * 2;
+    const uint4* osrc = reinterpret_cast<const uint4*>(ops + cta.op0);
+    uint4* odst = reinterpret_cast<uint4*>(ops_smem);
+    for (int i = threadIdx.x; i < nvec; i += kThreadsU) odst[i] = osrc[i];
+  }
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < ST; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], kConvWarps); mbar_init(&empty[s], 1); }
@@ -212,14 +230,17 @@ __global__ void __launch_bounds__(kThreadsU, 1)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  const UmProblem& p = *p_smem;
+  const int run_stages = (int)p.run_stages;
+  const int nruns = (nst + run_stages - 1) / run_stages;
+  const bool conv_a = p.A.convert != 0, conv_b = p.B.convert != 0;
+  const bool any_conv = conv_a || conv_b;
 
   const uint32_t a_bytes = p.A.part_bytes * p.A.nparts;
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer: lane q issues op q of the stage
     const int nops = (int)cta.ops_per_stage;
-    UmTmaOp op;
-    if (lane < nops && nst > 0) op = ops[cta.op0 + lane];
     for (int it = 0; it < nst; ++it) {
       const int s = it % ST;
       const uint32_t ph = (uint32_t)(it / ST) & 1u;
@@ -227,9 +248,10 @@ __global__ void __launch_bounds__(kThreadsU, 1)
       if (lane == 0) mbar_expect_tx(&full[s], cta.tx_bytes);
       __syncwarp();
       if (lane < nops) {
+        const int oi = it * nops + lane;
+        const UmTmaOp op = oi < kMaxOpsPerCta ? ops_smem[oi] : ops[cta.op0 + oi];
         const uint32_t dst = smem_u32(stage_base + (size_t)s * stage_bytes) + op.smem_off;
-        tma_load_5d(dst, maps + op.map, &full[s], op.c[0], op.c[1], op.c[2], op.c[3], op.c[4]);
-        if (it + 1 < nst) op = ops[cta.op0 + (size_t)(it + 1) * nops + lane];
+        tma_load_5d(dst, &maps.m[op.map], &full[s], op.c[0], op.c[1], op.c[2], op.c[3], op.c[4]);
       }
     }
     __syncwarp();

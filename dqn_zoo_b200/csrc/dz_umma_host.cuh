@@ -14,6 +14,8 @@ struct UmLaunch {
   int stages = 4;
   uint32_t stage_bytes = 0;
   bool convert = false;
+  int nmaps = 0;
+  int map_ids[um::kMaxMapsPerLaunch] = {0};   // plan map index of the launch-local map slot (the ops of this launch use slots)
 };
 
 struct UmPlan {
@@ -31,6 +33,8 @@ struct UmPlan {
   // `rank` are 1).  mn_major: the tile feeds an MN-major (transposing) descriptor -> 32-byte-atom flavour of the swizzle.
   // Returns the map index or -1 (error string set).
   int add_map(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, bool mn_major = false);
+  // Rewrites the `map` field of the ops of launch `l` (ctas [cta0, cta0 + nctas)) from plan indices to launch-local slots.
+  int localize_maps(UmLaunch& l);
   int upload();          // (re)allocates and copies all four tables
   void release();
   int launch(const char* tag, const UmLaunch& l, void* stream) const;

@@ -28,7 +28,12 @@ struct UmNet {
   // conv weight images: [blob][layer] K-major [N][K]; dgrad images (online)
   float *wf_hi[2][3], *wf_lo[2][3], *wd3_hi, *wd3_lo, *wd2_hi, *wd2_lo;
   int map_wf1[2][2];                              // [blob][hi/lo] for the conv1 kernel
-  UmLaunch l_conv2, l_conv3, l_dconv3, l_dconv2, l_fc, l_fcd;
+  UmLaunch l_conv2, l_conv3, l_dconv3, l_dconv2, l_fc, l_fcd, l_wconv3, l_wconv2;
+  float *wg3_part, *wg2_part, *wg1_part;   // conv3 / conv2 weight-gradient split partials [S][K][64]; conv1: one [256][32] per CTA
+  int wg3_splits, wg2_splits, wg1_ctas;
+  int map_g1[2];                           // dact1 hi / lo as a flat [B*h1*w1][32] tensor, 32-byte-atom swizzle
+  float* wg_scratch;                       // bias-gradient chunk sums [3][kWgMaxChunks][64]
+  unsigned int* wg_ticket;                 // [4]
   int conv1_stag_bytes, conv1_tiles_per_pass;
   // noise-dependent problem fields (patched when the caller's noise buffer moves)
   struct Patch { int prob; int field; int64_t off; };   // field 0: A.scale_r, 1: scale_i
@@ -101,26 +106,28 @@ __global__ void __launch_bounds__(256) um_pack_conv_kernel(const __grid_constant
 // add the bias, ReLU and write act1 as tf32 hi/lo (+ fp32).
 // ------------------------------------------------------------------------------------------------
 struct Conv1Args {
+  CUtensorMap wmap[2][2];          // weight image [blob][hi / lo] (grid-constant: descriptor fetch from the constant bank)
   const uint8_t* const* rows[3];
   const float* bias[3];
-  int map_hi[3], map_lo[3];
+  int blob[3];
   float *out_hi, *out_lo, *out_f32;
   int npass, B, W, oh, ow, m_pass, tiles_per_pass, ntiles, stag_bytes;
 };
 
 constexpr int kC1W = 65536, kC1A = 131072;
 
-__global__ void __launch_bounds__(kThreadsU, 1) conv1_umma_kernel(const __grid_constant__ Conv1Args a, const CUtensorMap* __restrict__ maps) {
+__global__ void __launch_bounds__(kThreadsU, 1) conv1_umma_kernel(const __grid_constant__ Conv1Args a) {
+  if (threadIdx.x < 4) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.wmap[threadIdx.x >> 1][threadIdx.x & 1])) : "memory");
   dz::pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint64_t* raw_full = reinterpret_cast<uint64_t*>(smem);   // [2]
-  uint64_t* raw_empty = raw_full + 2;                        // [2]
-  uint64_t* w_full = raw_empty + 2;
-  uint64_t* a_ready = w_full + 1;
-  uint64_t* a_empty = a_ready + 1;
-  uint64_t* acc_full = a_empty + 1;                          // [2]
+  uint64_t* raw_full = reinterpret_cast<uint64_t*>(smem);   // [2] staged input rows landed
+  uint64_t* raw_empty = raw_full + 2;                        // [2] converters are done reading them
+  uint64_t* w_full = raw_empty + 2;                          // [1] weight image landed (only reloaded when the pass changes)
+  uint64_t* a_ready = w_full + 1;                            // [4] kernel-row pair (2j, 2j+1) of the A tile converted
+  uint64_t* a_empty = a_ready + 4;                           // [4] ... consumed by the MMAs
+  uint64_t* acc_full = a_empty + 4;                          // [2]
   uint64_t* acc_empty = acc_full + 2;                        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   uint8_t* w_smem = smem + 1024;
@@ -131,7 +138,8 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_umma_kernel(const __grid_c
   if (warp == 1) {
     if (lane == 0) {
       for (int b = 0; b < 2; ++b) { mbar_init(&raw_full[b], 1); mbar_init(&raw_empty[b], kConvWarps); mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
-      mbar_init(w_full, 1); mbar_init(a_ready, kConvWarps); mbar_init(a_empty, 1);
+      for (int j = 0; j < 4; ++j) { mbar_init(&a_ready[j], kConvWarps); mbar_init(&a_empty[j], 1); }
+      mbar_init(w_full, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -145,11 +153,14 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_umma_kernel(const __grid_c
 
   const int px = a.oh * a.ow;             // output pixels per image
   const int row_bytes = a.W * 4;          // one input row of 4-channel pixels
+  // consecutive tiles per CTA: the weight image is reloaded only when the pass (online / target parameters) changes
+  const int t_begin = (int)(((long long)blockIdx.x * a.ntiles) / gridDim.x);
+  const int t_end = (int)(((long long)(blockIdx.x + 1) * a.ntiles) / gridDim.x);
 
   if (warp == 0) {
     // ---------------------------------------------------------------- producer
-    int n = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++n) {
+    int cur_pass = -1;
+    for (int tile = t_begin, n = 0; tile < t_end; ++tile, ++n) {
       const int buf = n & 1;
       const int pass = tile / a.tiles_per_pass;
       const int m0 = (tile - pass * a.tiles_per_pass) * 128, m1 = min(m0 + 128, a.m_pass);
@@ -172,24 +183,27 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_umma_kernel(const __grid_c
           off += bytes;
         }
       }
-      mbar_wait(a_empty, ((uint32_t)n & 1u) ^ 1u);    // previous tile's MMAs are done with the weight image
-      if (lane == 0) mbar_expect_tx(w_full, (uint32_t)kC1W);
-      __syncwarp();
-      if (lane < 16) {
-        const int part = lane >> 3, s = lane & 7;
-        tma_load_5d(smem_u32(w_smem) + part * 32768 + s * 4096, maps + (part ? a.map_lo[pass] : a.map_hi[pass]), w_full, 32 * s, 0, 0, 0, 0);
+      if (pass != cur_pass) {
+        if (n > 0) mbar_wait(&a_empty[3], ((uint32_t)(n - 1)) & 1u);   // previous tile's MMAs are done with the old image
+        if (lane == 0) mbar_expect_tx(w_full, (uint32_t)kC1W);
+        __syncwarp();
+        if (lane < 16) {
+          const int part = lane >> 3, s = lane & 7;
+          tma_load_5d(smem_u32(w_smem) + part * 32768 + s * 4096, &a.wmap[a.blob[pass]][part], w_full, 32 * s, 0, 0, 0, 0);
+        }
+        cur_pass = pass;
       }
       __syncwarp();
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
     const uint32_t idesc = make_idesc(128, 32, 0, 0);
-    int n = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++n) {
-      mbar_wait(a_ready, (uint32_t)n & 1u);
-      mbar_wait(w_full, (uint32_t)n & 1u);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    int cur_pass = -1, wn = 0;
+    for (int tile = t_begin, n = 0; tile < t_end; ++tile, ++n) {
+      const int pass = tile / a.tiles_per_pass;
+      if (pass != cur_pass) { mbar_wait(w_full, (uint32_t)wn & 1u); ++wn; cur_pass = pass; }
       for (int slab = 0; slab < 8; ++slab) {
+        if ((slab & 1) == 0) mbar_wait(&a_ready[slab >> 1], (uint32_t)n & 1u);
         const int g = n * 8 + slab, buf = g & 1;
         mbar_wait(&acc_empty[buf], (((uint32_t)g >> 1) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -203,7 +217,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_umma_kernel(const __grid_c
             mma_tf32(d, da, make_desc_sw128(wh + k * 32, 16, 1024), idesc, 1u);
           }
           mma_commit(&acc_full[buf]);
-          if (slab == 7) mma_commit(a_empty);
+          if (slab & 1) mma_commit(&a_empty[slab >> 1]);
         }
         __syncwarp();
       }
@@ -211,8 +225,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_umma_kernel(const __grid_c
   } else if (warp < 6) {
     // ---------------------------------------------------------------- epilogue
     const int quarter = warp & 3;
-    int n = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++n) {
+    for (int tile = t_begin, n = 0; tile < t_end; ++tile, ++n) {
       const int pass = tile / a.tiles_per_pass;
       const int m0 = (tile - pass * a.tiles_per_pass) * 128, m1 = min(m0 + 128, a.m_pass);
       float sum[32];
@@ -251,8 +264,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_umma_kernel(const __grid_c
     // ---------------------------------------------------------------- converters: uint8 rows -> exact tf32 A tile
     const int ct = threadIdx.x - 6 * 32;
     const int r = ct & 127, khp = ct >> 7;
-    int n = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++n) {
+    for (int tile = t_begin, n = 0; tile < t_end; ++tile, ++n) {
       const int buf = n & 1;
       const int pass = tile / a.tiles_per_pass;
       const int m0 = (tile - pass * a.tiles_per_pass) * 128, m1 = min(m0 + 128, a.m_pass);
@@ -271,7 +283,6 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_umma_kernel(const __grid_c
         src_off = off + (4 * (oy - plo / a.ow)) * row_bytes + 16 * ox;
       }
       mbar_wait(&raw_full[buf], ((uint32_t)n >> 1) & 1u);
-      mbar_wait(a_empty, ((uint32_t)n & 1u) ^ 1u);      // previous tile's MMAs have consumed the A tile
       const uint8_t* src = stag + (size_t)buf * a.stag_bytes + src_off;
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
@@ -283,6 +294,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_umma_kernel(const __grid_c
         } else {
           u[0] = make_uint4(0, 0, 0, 0); u[1] = u[0];
         }
+        mbar_wait(&a_empty[it], ((uint32_t)n & 1u) ^ 1u);     // the previous tile's MMAs have consumed this kernel-row pair
         uint8_t* dstrow = a_smem + kh * 16384 + r * 128;
         const uint32_t w[8] = {u[0].x, u[0].y, u[0].z, u[0].w, u[1].x, u[1].y, u[1].z, u[1].w};
 #pragma unroll
@@ -295,16 +307,219 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_umma_kernel(const __grid_c
           f.w = __uint_as_float(__byte_perm(w[kw], 0x4B000000u, 0x7443)) - 8388608.0f;
           *reinterpret_cast<float4*>(dstrow + ((kw ^ (r & 7)) << 4)) = f;
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[it]);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) { mbar_arrive(a_ready); mbar_arrive(&raw_empty[buf]); }
+      if (lane == 0) mbar_arrive(&raw_empty[buf]);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv1 weight gradient: dW1[k][n] = (1/255) * sum_m X[m][k] * dact1[m][n], reduction over the B * h1 * w1 output pixels of
+// pass 0.  Same staging as the forward kernel (bulk-copied uint8 rows -> exact tf32 A tile), but the tile is written in
+// the 32-byte-atom swizzle and consumed through MN-major descriptors (rows = reduction index): A^T is never formed.
+// G = dact1 hi/lo arrives by TMA.  Two accumulators (k 0..127 | 128..255) x two TMEM buffers; one partial per CTA.
+// ------------------------------------------------------------------------------------------------
+struct Conv1WgArgs {
+  CUtensorMap gmap[2];             // dact1 hi / lo
+  const uint8_t* const* rows;
+  float* partial;                // [gridDim.x][256][32]
+  int B, W, oh, ow, m_pass, ntiles, stag_bytes;
+};
+
+constexpr int kC1G = 32768;      // dact1 tile: hi | lo, [128 rows][32 n] each
+
+__global__ void __launch_bounds__(kThreadsU, 1) conv1_wgrad_umma_kernel(const __grid_constant__ Conv1WgArgs a) {
+  if (threadIdx.x < 2) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.gmap[threadIdx.x])) : "memory");
+  dz::pdl_enter();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint64_t* raw_full = reinterpret_cast<uint64_t*>(smem);   // [2]
+  uint64_t* raw_empty = raw_full + 2;                        // [2]
+  uint64_t* g_full = raw_empty + 2;                          // [1] dact1 tile landed
+  uint64_t* a_ready = g_full + 1;                            // [4] kernel-row pairs converted
+  uint64_t* t_done = a_ready + 4;                            // [1] all MMAs of the tile done (A and G tiles free)
+  uint64_t* acc_full = t_done + 1;                           // [2]
+  uint64_t* acc_empty = acc_full + 2;                        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint8_t* g_smem = smem + 1024;
+  uint8_t* a_smem = g_smem + kC1G;
+  uint8_t* stag = a_smem + kC1A;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int b = 0; b < 2; ++b) { mbar_init(&raw_full[b], 1); mbar_init(&raw_empty[b], kConvWarps); mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+      for (int j = 0; j < 4; ++j) mbar_init(&a_ready[j], kConvWarps);
+      mbar_init(g_full, 1); mbar_init(t_done, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int px = a.oh * a.ow;
+  const int row_bytes = a.W * 4;
+  const int t_begin = (int)(((long long)blockIdx.x * a.ntiles) / gridDim.x);
+  const int t_end = (int)(((long long)(blockIdx.x + 1) * a.ntiles) / gridDim.x);
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- producer
+    for (int tile = t_begin, n = 0; tile < t_end; ++tile, ++n) {
+      const int buf = n & 1;
+      const int m0 = tile * 128, m1 = min(m0 + 128, a.m_pass);
+      mbar_wait(&raw_empty[buf], (((uint32_t)n >> 1) & 1u) ^ 1u);
+      if (lane == 0) {
+        const int b0 = m0 / px, b1 = (m1 - 1) / px;
+        uint32_t total = 0;
+        for (int b = b0; b <= b1; ++b) {
+          const int plo = max(m0, b * px) - b * px, phi = min(m1, (b + 1) * px) - b * px;
+          total += (uint32_t)((4 * ((phi - 1) / a.ow - plo / a.ow) + 8) * row_bytes);
+        }
+        mbar_expect_tx(&raw_full[buf], total);
+        uint32_t off = 0;
+        const uint32_t dst0 = smem_u32(stag + (size_t)buf * a.stag_bytes);
+        for (int b = b0; b <= b1; ++b) {
+          const int plo = max(m0, b * px) - b * px, phi = min(m1, (b + 1) * px) - b * px;
+          const int oy0 = plo / a.ow;
+          const uint32_t bytes = (uint32_t)((4 * ((phi - 1) / a.ow - oy0) + 8) * row_bytes);
+          bulk_g2s(dst0 + off, a.rows[b] + (size_t)(4 * oy0) * row_bytes, bytes, &raw_full[buf]);
+          off += bytes;
+        }
+      }
+      if (n > 0) mbar_wait(t_done, ((uint32_t)(n - 1)) & 1u);
+      if (lane == 0) mbar_expect_tx(g_full, (uint32_t)kC1G);
+      __syncwarp();
+      if (lane < 2) tma_load_5d(smem_u32(g_smem) + lane * 16384, &a.gmap[lane], g_full, 0, m0, 0, 0, 0);
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    const uint32_t idesc = make_idesc(128, 32, 1, 1);     // both operands MN-major (rows of the tiles are the reduction)
+    for (int tile = t_begin, n = 0; tile < t_end; ++tile, ++n) {
+      mbar_wait(g_full, (uint32_t)n & 1u);
+      for (int mt = 0; mt < 2; ++mt) {                      // k 0..127 (kernel rows 0-3) | k 128..255 (kernel rows 4-7)
+        mbar_wait(&a_ready[2 * mt], (uint32_t)n & 1u);
+        mbar_wait(&a_ready[2 * mt + 1], (uint32_t)n & 1u);
+        const int g = n * 2 + mt, buf = g & 1;
+        mbar_wait(&acc_empty[buf], (((uint32_t)g >> 1) & 1u) ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint32_t ab = smem_u32(a_smem) + mt * 4 * 16384, gh = smem_u32(g_smem), gl = gh + 16384;
+          const uint32_t d = tmem_base + (uint32_t)(buf * 64 + mt * 32);
+#pragma unroll 4
+          for (int k = 0; k < 16; ++k) {
+            const uint64_t da = make_desc_sw128(ab + k * 1024, 16384, 512, 1);
+            mma_tf32(d, da, make_desc_sw128(gl + k * 1024, 16384, 512, 1), idesc, k > 0 ? 1u : 0u);
+            mma_tf32(d, da, make_desc_sw128(gh + k * 1024, 16384, 512, 1), idesc, 1u);
+          }
+          mma_commit(&acc_full[buf]);
+          if (mt == 1) mma_commit(t_done);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 6) {
+    // ---------------------------------------------------------------- epilogue: rows k of both accumulators
+    const int quarter = warp & 3;
+    float sum[2][32];
+#pragma unroll
+    for (int t = 0; t < 32; ++t) { sum[0][t] = 0.f; sum[1][t] = 0.f; }
+    for (int tile = t_begin, n = 0; tile < t_end; ++tile, ++n) {
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int g = n * 2 + mt, buf = g & 1;
+        mbar_wait(&acc_full[buf], ((uint32_t)g >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 64 + mt * 32), r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int t = 0; t < 32; ++t) sum[mt][t] += __uint_as_float(r[t]);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      }
+    }
+    const float inv255 = 0.0039215688593685627f;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      float* dst = a.partial + ((long long)blockIdx.x * 256 + mt * 128 + quarter * 32 + lane) * 32;
+#pragma unroll
+      for (int t = 0; t < 32; t += 4)
+        *reinterpret_cast<float4*>(dst + t) = make_float4(sum[mt][t] * inv255, sum[mt][t + 1] * inv255, sum[mt][t + 2] * inv255, sum[mt][t + 3] * inv255);
+    }
+  } else {
+    // ---------------------------------------------------------------- converters
+    const int ct = threadIdx.x - 6 * 32;
+    const int r = ct & 127, khp = ct >> 7;
+    for (int tile = t_begin, n = 0; tile < t_end; ++tile, ++n) {
+      const int buf = n & 1;
+      const int m0 = tile * 128, m1 = min(m0 + 128, a.m_pass);
+      const int m = m0 + r;
+      const bool valid = m < m1;
+      int src_off = 0;
+      if (valid) {
+        const int b0 = m0 / px, b = m / px, p = m - b * px, oy = p / a.ow, ox = p - oy * a.ow;
+        int off = 0;
+        for (int bb = b0; bb < b; ++bb) {
+          const int plo = max(m0, bb * px) - bb * px, phi = min(m1, (bb + 1) * px) - bb * px;
+          off += (4 * ((phi - 1) / a.ow - plo / a.ow) + 8) * row_bytes;
+        }
+        const int plo = max(m0, b * px) - b * px;
+        src_off = off + (4 * (oy - plo / a.ow)) * row_bytes + 16 * ox;
+      }
+      mbar_wait(&raw_full[buf], ((uint32_t)n >> 1) & 1u);
+      if (n > 0) mbar_wait(t_done, ((uint32_t)(n - 1)) & 1u);     // previous tile's MMAs have consumed the A tile
+      const uint8_t* src = stag + (size_t)buf * a.stag_bytes + src_off;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int kh = 2 * it + khp;
+        uint4 u[2];
+        if (valid) {
+          u[0] = *reinterpret_cast<const uint4*>(src + kh * row_bytes);
+          u[1] = *reinterpret_cast<const uint4*>(src + kh * row_bytes + 16);
+        } else {
+          u[0] = make_uint4(0, 0, 0, 0); u[1] = u[0];     // rows beyond the batch contribute zeros to the reduction
+        }
+        uint8_t* dstrow = a_smem + kh * 16384 + r * 128;
+        const uint32_t w[8] = {u[0].x, u[0].y, u[0].z, u[0].w, u[1].x, u[1].y, u[1].z, u[1].w};
+#pragma unroll
+        for (int kw = 0; kw < 8; ++kw) {
+          float4 f;
+          f.x = __uint_as_float(__byte_perm(w[kw], 0x4B000000u, 0x7440)) - 8388608.0f;
+          f.y = __uint_as_float(__byte_perm(w[kw], 0x4B000000u, 0x7441)) - 8388608.0f;
+          f.z = __uint_as_float(__byte_perm(w[kw], 0x4B000000u, 0x7442)) - 8388608.0f;
+          f.w = __uint_as_float(__byte_perm(w[kw], 0x4B000000u, 0x7443)) - 8388608.0f;
+          // 128B swizzle with 32-byte atoms: the 32-byte chunk index is XOR-ed with (row & 3)
+          *reinterpret_cast<float4*>(dstrow + ((((kw >> 1) ^ (r & 3)) << 5) | ((kw & 1) << 4))) = f;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[it]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&raw_empty[buf]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
   }
 }
 
@@ -371,6 +586,60 @@ __global__ void __launch_bounds__(256) um_fcd_finish_kernel(const float* __restr
     *reinterpret_cast<float4*>(out + i) = v;
     *reinterpret_cast<float4*>(out_hi + i) = h;
     *reinterpret_cast<float4*>(out_lo + i) = l;
+  }
+}
+
+
+// Weight-gradient finish: dW[k][n] = sum_s partial[s][k][n] (fixed order), and the bias gradient db[n] = sum_m G[m][n]
+// as a deterministic two-level column sum of the (fp32) output gradient: 128-row chunks in parallel, the last block to
+// finish adds the chunk sums in chunk order.  One launch covers several layers: blockIdx.y = layer; blocks
+// [0, kWgSumBlocks) add the partials, blocks beyond do the bias chunks.
+constexpr int kWgSumBlocks = 36, kWgChunkRows = 128, kWgMaxChunks = 256;
+struct WgFinish { const float* partial; int S; long long stride; int KN; float* dW; const float* G; int M, N; float* db; float* scratch; unsigned int* ticket; };
+struct WgFinishBatch { WgFinish f[4]; int n; };
+
+__global__ void __launch_bounds__(256) um_wgrad_finish_kernel(const __grid_constant__ WgFinishBatch b) {
+  dz::pdl_enter();
+  const WgFinish& f = b.f[blockIdx.y];
+  __shared__ float red[256];
+  __shared__ bool last;
+  if (blockIdx.x >= kWgSumBlocks) {
+    const int chunk = blockIdx.x - kWgSumBlocks, nchunks = (f.M + kWgChunkRows - 1) / kWgChunkRows;
+    if (!f.db || chunk >= nchunks) return;
+    const int n = threadIdx.x % f.N, g = threadIdx.x / f.N, G = 256 / f.N;
+    const int m1 = min(f.M, (chunk + 1) * kWgChunkRows);
+    float acc = 0.f;
+    for (int m = chunk * kWgChunkRows + g; m < m1; m += G) acc += f.G[(long long)m * f.N + n];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < f.N) {
+      float t = 0.f;
+      for (int q = 0; q < G; ++q) t += red[q * f.N + threadIdx.x];
+      f.scratch[chunk * 64 + threadIdx.x] = t;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(f.ticket, 1u) == (unsigned)(nchunks - 1);
+    __syncthreads();
+    if (last) {
+      __threadfence();
+      if (threadIdx.x < f.N) {
+        float t = 0.f;
+        for (int c = 0; c < nchunks; ++c) t += ((volatile float*)f.scratch)[c * 64 + threadIdx.x];
+        f.db[threadIdx.x] = t;
+      }
+      if (threadIdx.x == 0) *f.ticket = 0;
+    }
+    return;
+  }
+  const int total4 = f.KN >> 2;
+  for (int i4 = blockIdx.x * 256 + threadIdx.x; i4 < total4; i4 += kWgSumBlocks * 256) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < f.S; ++s) {
+      const float4 x = *reinterpret_cast<const float4*>(f.partial + s * f.stride + ((long long)i4 << 2));
+      v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+    }
+    *reinterpret_cast<float4*>(f.dW + ((long long)i4 << 2)) = v;
   }
 }
 
@@ -447,6 +716,18 @@ int64_t carve_net(UmNet* n, char* base) {
     for (int L = 0; L < 3; ++L) { n->wf_hi[b][L] = c.f(kN[L] * kK[L]); n->wf_lo[b][L] = c.f(kN[L] * kK[L]); }
   n->wd3_hi = c.f(64 * 576); n->wd3_lo = c.f(64 * 576);
   n->wd2_hi = c.f(128 * 256); n->wd2_lo = c.f(128 * 256);
+  {
+    const int groups = (d.B + 7) / 8;
+    n->wg3_splits = std::max(1, std::min(g.h3, 148 / 5));             // stages = h3 * groups, split over the output rows
+    n->wg2_splits = std::max(1, std::min(g.h2, 148 / 8));
+    (void)groups;
+    n->wg3_part = c.f((int64_t)n->wg3_splits * 576 * 64);
+    n->wg2_part = c.f((int64_t)n->wg2_splits * 512 * 64);
+    n->wg1_ctas = std::min(148, (d.B * g.h1 * g.w1 + 127) / 128);
+    n->wg1_part = c.f((int64_t)n->wg1_ctas * 256 * 32);
+    n->wg_scratch = c.f(3 * 256 * 64);
+    n->wg_ticket = reinterpret_cast<unsigned int*>(c.f(64));
+  }
   n->h1_buf = nullptr; n->dh1_f32 = n->dh1_hi = n->dh1_lo = nullptr; n->fc_part = n->fcd_part = nullptr;
   n->fc_nprob = n->fcd_nsrc = 0; n->fc_splits = n->fcd_splits = 1;
   if (d.use_fc) {
@@ -509,7 +790,7 @@ int build_plan(UmNet* n) {
     n->l_conv2.cta0 = (int)pl.ctas.size(); n->l_conv2.njt = 64; n->l_conv2.stage_bytes = a_bytes + Bo.part_bytes * 2;
     // the MMA reads 128 rows of every A part: keep the (garbage) tail rows inside the stage
     n->l_conv2.stage_bytes = std::max<uint32_t>(n->l_conv2.stage_bytes, A.part_bytes + 16384);
-    n->l_conv2.stages = std::min<int>(kStagesMax, (int)((225 * 1024 - 2048) / n->l_conv2.stage_bytes));
+    n->l_conv2.stages = std::min<int>(kStagesMax, (int)((226 * 1024 - 1024 - kCtlBytes) / n->l_conv2.stage_bytes));
     for (int p = 0; p < d.npass; ++p) {
       const int blob = d.pass_target[p] ? 1 : 0;
       UmProblem pr;
@@ -556,7 +837,7 @@ int build_plan(UmNet* n) {
     const uint32_t a_bytes = A.part_bytes * 2;
     n->l_conv3.cta0 = (int)pl.ctas.size(); n->l_conv3.njt = 32;
     n->l_conv3.stage_bytes = std::max<uint32_t>(a_bytes + Bo.part_bytes * 2, A.part_bytes + 16384);
-    n->l_conv3.stages = std::min<int>(kStagesMax, (int)((225 * 1024 - 2048) / n->l_conv3.stage_bytes));
+    n->l_conv3.stages = std::min<int>(kStagesMax, (int)((226 * 1024 - 1024 - kCtlBytes) / n->l_conv3.stage_bytes));
     for (int p = 0; p < d.npass; ++p) {
       const int blob = d.pass_target[p] ? 1 : 0;
       for (int half = 0; half < 2; ++half) {
@@ -612,7 +893,7 @@ int build_plan(UmNet* n) {
     const uint32_t a_bytes = A.part_bytes * 2;
     n->l_dconv3.cta0 = (int)pl.ctas.size(); n->l_dconv3.njt = 32;
     n->l_dconv3.stage_bytes = std::max<uint32_t>(a_bytes + Bo.part_bytes * 2, A.part_bytes + 16384);
-    n->l_dconv3.stages = std::min<int>(kStagesMax, (int)((225 * 1024 - 2048) / n->l_dconv3.stage_bytes));
+    n->l_dconv3.stages = std::min<int>(kStagesMax, (int)((226 * 1024 - 1024 - kCtlBytes) / n->l_dconv3.stage_bytes));
     for (int half = 0; half < 2; ++half) {
       UmProblem pr;
       memset(&pr, 0, sizeof(pr));
@@ -665,7 +946,7 @@ int build_plan(UmNet* n) {
     const uint32_t a_bytes = A.part_bytes * 2;
     n->l_dconv2.cta0 = (int)pl.ctas.size(); n->l_dconv2.njt = 32;
     n->l_dconv2.stage_bytes = std::max<uint32_t>(a_bytes + Bo.part_bytes * 2, A.part_bytes + 16384);
-    n->l_dconv2.stages = std::min<int>(kStagesMax, (int)((225 * 1024 - 2048) / n->l_dconv2.stage_bytes));
+    n->l_dconv2.stages = std::min<int>(kStagesMax, (int)((226 * 1024 - 1024 - kCtlBytes) / n->l_dconv2.stage_bytes));
     UmProblem pr;
     memset(&pr, 0, sizeof(pr));
     pr.A = A; pr.B = Bo; pr.ksteps = 4; pr.run_stages = 2; pr.red_per_stage = 32; pr.epi = UM_EPI_ROWS;
@@ -693,6 +974,124 @@ int build_plan(UmNet* n) {
         pl.ctas.push_back(c);
       }
     n->l_dconv2.nctas = (int)pl.ctas.size() - n->l_dconv2.cta0;
+  }
+
+  for (int part = 0; part < 2; ++part) {   // conv1 weight gradient: G operand
+    uint64_t dims[2] = {32, (uint64_t)B * h1 * w1}, strides[1] = {128};
+    uint32_t box[2] = {32, 128};
+    n->map_g1[part] = pl.add_map(part ? n->dact_lo[0] : n->dact_hi[0], 2, dims, strides, box, true);
+    if (n->map_g1[part] < 0) return DZ_EINVAL;
+  }
+  // =========================================================================== conv3 / conv2 weight gradients
+  // dW[k][n] = sum_m A[m][k] G[m][n]: both operands are read through MN-major (transposing) descriptors straight from the
+  // NHWC tensors — the same im2col boxes as the forward pass, with the reduction running over (output row, 8 images).
+  {
+    const int groups = (B + 7) / 8;
+    // ---- conv3: A = act2 patches (pass 0), G = dact3
+    {
+      int m_a[2], m_g[2];
+      for (int part = 0; part < 2; ++part) {
+        uint64_t dims[4] = {64, (uint64_t)w2, (uint64_t)h2, (uint64_t)PB};
+        uint64_t strides[3] = {256, (uint64_t)w2 * 256, (uint64_t)h2 * w2 * 256};
+        uint32_t box[4] = {32, (uint32_t)w3, 1, 8};
+        m_a[part] = pl.add_map(part ? n->act_lo[1] : n->act_hi[1], 4, dims, strides, box, true);
+        uint64_t gd[4] = {64, (uint64_t)w3, (uint64_t)h3, (uint64_t)B};
+        uint64_t gs[3] = {256, (uint64_t)w3 * 256, (uint64_t)h3 * w3 * 256};
+        m_g[part] = pl.add_map(part ? n->dact_lo[2] : n->dact_hi[2], 4, gd, gs, box, true);
+        if (m_a[part] < 0 || m_g[part] < 0) return DZ_EINVAL;
+      }
+      const int rows = w3 * 8;                                  // reduction rows per stage (multiple of 8)
+      UmOperand A = um_mnmajor(128, rows, false), Bo = um_mnmajor(64, rows, false);
+      const uint32_t a_bytes = A.part_bytes * 2;
+      n->l_wconv3.cta0 = (int)pl.ctas.size(); n->l_wconv3.njt = 64;
+      n->l_wconv3.stage_bytes = (a_bytes + Bo.part_bytes * 2 + 1023) / 1024 * 1024;
+      n->l_wconv3.stages = std::max(1, std::min<int>(kStagesMax, (int)((226 * 1024 - 1024 - kCtlBytes) / n->l_wconv3.stage_bytes)));
+      UmProblem pr;
+      memset(&pr, 0, sizeof(pr));
+      pr.A = A; pr.B = Bo; pr.ksteps = (uint32_t)(rows / 8); pr.run_stages = 1; pr.red_per_stage = (uint32_t)rows;
+      pr.epi = UM_EPI_PARTIAL; pr.MI = 576; pr.NJ = 64;
+      pr.C = n->wg3_part; pr.sc_i = 64; pr.sc_j = 1; pr.split_stride = 576 * 64;
+      const int prob = (int)pl.probs.size();
+      pl.probs.push_back(pr);
+      const int S = n->wg3_splits, per = (h3 + S - 1) / S;
+      for (int kt = 0; kt < 5; ++kt)                            // 18 slabs of 32 reduction... k values: 4,4,4,4,2
+        for (int sp = 0; sp < S; ++sp) {
+          const int oy0 = sp * per, oy1 = std::min(h3, oy0 + per);
+          if (oy1 <= oy0) continue;
+          UmCta c;
+          memset(&c, 0, sizeof(c));
+          const int nslab = std::min(4, 18 - kt * 4);
+          c.prob = (uint32_t)prob; c.op0 = (uint32_t)pl.ops.size(); c.nstages = (uint32_t)((oy1 - oy0) * groups);
+          c.ops_per_stage = (uint32_t)(2 * nslab + 4);
+          c.tx_bytes = (uint32_t)((2 * nslab + 4) * rows * 128);
+          c.i0 = kt * 128; c.split = sp;
+          for (int oy = oy0; oy < oy1; ++oy)
+            for (int gidx = 0; gidx < groups; ++gidx) {
+              for (int part = 0; part < 2; ++part)
+                for (int sl = 0; sl < nslab; ++sl) {
+                  const int slab = kt * 4 + sl, tap = slab >> 1, ch = slab & 1, kh = tap / 3, kw = tap % 3;
+                  push_op(pl, m_a[part], part * A.part_bytes + sl * A.lbo, 32 * ch, kw, oy + kh, gidx * 8, 0);
+                }
+              for (int part = 0; part < 2; ++part)
+                for (int nh = 0; nh < 2; ++nh) push_op(pl, m_g[part], a_bytes + part * Bo.part_bytes + nh * Bo.lbo, 32 * nh, 0, oy, gidx * 8, 0);
+            }
+          pl.ctas.push_back(c);
+        }
+      n->l_wconv3.nctas = (int)pl.ctas.size() - n->l_wconv3.cta0;
+    }
+    // ---- conv2: A = act1 patches through the stride-2 parity view (pass 0), G = dact2; two 32-column halves
+    {
+      int m_a[2], m_g[2];
+      for (int part = 0; part < 2; ++part) {
+        uint64_t dims[5] = {64, (uint64_t)w1 / 2, 2, (uint64_t)h1 / 2, (uint64_t)PB};
+        uint64_t strides[4] = {256, (uint64_t)w1 * 128, (uint64_t)2 * w1 * 128, (uint64_t)h1 * w1 * 128};
+        uint32_t box[5] = {32, (uint32_t)w2, 1, 1, 8};
+        m_a[part] = pl.add_map(part ? n->act_lo[0] : n->act_hi[0], 5, dims, strides, box, true);
+        uint64_t gd[4] = {64, (uint64_t)w2, (uint64_t)h2, (uint64_t)B};
+        uint64_t gs[3] = {256, (uint64_t)w2 * 256, (uint64_t)h2 * w2 * 256};
+        uint32_t gbox[4] = {32, (uint32_t)w2, 1, 8};
+        m_g[part] = pl.add_map(part ? n->dact_lo[1] : n->dact_hi[1], 4, gd, gs, gbox, true);
+        if (m_a[part] < 0 || m_g[part] < 0) return DZ_EINVAL;
+      }
+      const int rows = w2 * 8;
+      UmOperand A = um_mnmajor(128, rows, false), Bo = um_mnmajor(32, rows, false);
+      const uint32_t a_bytes = A.part_bytes * 2;
+      n->l_wconv2.cta0 = (int)pl.ctas.size(); n->l_wconv2.njt = 32;
+      n->l_wconv2.stage_bytes = (a_bytes + Bo.part_bytes * 2 + 1023) / 1024 * 1024;
+      n->l_wconv2.stages = std::max(1, std::min<int>(kStagesMax, (int)((226 * 1024 - 1024 - kCtlBytes) / n->l_wconv2.stage_bytes)));
+      const int S = n->wg2_splits, per = (h2 + S - 1) / S;
+      for (int half = 0; half < 2; ++half) {
+        UmProblem pr;
+        memset(&pr, 0, sizeof(pr));
+        pr.A = A; pr.B = Bo; pr.ksteps = (uint32_t)(rows / 8); pr.run_stages = 1; pr.red_per_stage = (uint32_t)rows;
+        pr.epi = UM_EPI_PARTIAL; pr.MI = 512; pr.NJ = 32;
+        pr.C = n->wg2_part + 32 * half; pr.sc_i = 64; pr.sc_j = 1; pr.split_stride = 512 * 64;
+        const int prob = (int)pl.probs.size();
+        pl.probs.push_back(pr);
+        for (int kt = 0; kt < 4; ++kt)
+          for (int sp = 0; sp < S; ++sp) {
+            const int oy0 = sp * per, oy1 = std::min(h2, oy0 + per);
+            if (oy1 <= oy0) continue;
+            UmCta c;
+            memset(&c, 0, sizeof(c));
+            c.prob = (uint32_t)prob; c.op0 = (uint32_t)pl.ops.size(); c.nstages = (uint32_t)((oy1 - oy0) * groups);
+            c.ops_per_stage = 10;
+            c.tx_bytes = (uint32_t)(10 * rows * 128);
+            c.i0 = kt * 128; c.split = sp;
+            for (int oy = oy0; oy < oy1; ++oy)
+              for (int gidx = 0; gidx < groups; ++gidx) {
+                for (int part = 0; part < 2; ++part)
+                  for (int sl = 0; sl < 4; ++sl) {
+                    const int tap = kt * 4 + sl, kh = tap >> 2, kw = tap & 3;   // one slab = one (kh, kw) tap x 32 channels
+                    push_op(pl, m_a[part], part * A.part_bytes + sl * A.lbo, 32 * (kw & 1), kw >> 1, kh & 1, oy + (kh >> 1), gidx * 8);
+                  }
+                for (int part = 0; part < 2; ++part) push_op(pl, m_g[part], a_bytes + part * Bo.part_bytes, 32 * half, 0, oy, gidx * 8, 0);
+              }
+            pl.ctas.push_back(c);
+          }
+      }
+      n->l_wconv2.nctas = (int)pl.ctas.size() - n->l_wconv2.cta0;
+    }
   }
 
   // =========================================================================== fc1 / noisy1 forward and input gradient
@@ -732,7 +1131,7 @@ int build_plan(UmNet* n) {
       const int nk = feat / 32, S = n->fc_splits, per = (nk + S - 1) / S;
       n->l_fc.cta0 = (int)pl.ctas.size(); n->l_fc.njt = njt; n->l_fc.convert = true;
       n->l_fc.stage_bytes = 2 * 16384 + 2 * Bo.part_bytes;
-      n->l_fc.stages = std::min<int>(kStagesMax, (int)((225 * 1024 - 2048) / n->l_fc.stage_bytes));
+      n->l_fc.stages = std::min<int>(kStagesMax, (int)((226 * 1024 - 1024 - kCtlBytes) / n->l_fc.stage_bytes));
       for (int p = 0; p < d.npass; ++p) {
         const int blob = d.pass_target[p] ? 1 : 0;
         for (int s = 0; s < d.nstream; ++s)
@@ -771,7 +1170,7 @@ int build_plan(UmNet* n) {
       const int S = n->fcd_splits, per = (16 + S - 1) / S, ktiles = (feat + 127) / 128;
       n->l_fcd.cta0 = (int)pl.ctas.size(); n->l_fcd.njt = njt; n->l_fcd.convert = true;
       n->l_fcd.stage_bytes = 2 * 16384 + 2 * Bo.part_bytes;
-      n->l_fcd.stages = std::min<int>(kStagesMax, (int)((225 * 1024 - 2048) / n->l_fcd.stage_bytes));
+      n->l_fcd.stages = std::min<int>(kStagesMax, (int)((226 * 1024 - 1024 - kCtlBytes) / n->l_fcd.stage_bytes));
       for (int s = 0; s < d.nstream; ++s)
         for (int sg = 0; sg < q; ++sg) {
           const int src = s * q + sg;
@@ -850,18 +1249,23 @@ int um_net_create(const UmNetDesc& d, char* base, UmNet** out) {
     worst = std::max(worst, tot);
   }
   n->conv1_stag_bytes = (worst + 1023) / 1024 * 1024;
+  cudaMemset(n->wg_ticket, 0, 64 * 4);
   // gradient buffers start as zeros (hi/lo pairs of layers whose producer has not run yet are never NaN)
   for (int L = 0; L < 3; ++L) {
     const int64_t cnt[3] = {(int64_t)d.B * n->h1 * n->w1 * 32, (int64_t)d.B * n->h2 * n->w2 * 64, (int64_t)d.B * n->feat};
     cudaMemset(n->dact_hi[L], 0, cnt[L] * 4); cudaMemset(n->dact_lo[L], 0, cnt[L] * 4); cudaMemset(n->dact_f32[L], 0, cnt[L] * 4);
   }
   int rc = build_plan(n);
+  UmLaunch* all[8] = {&n->l_conv2, &n->l_conv3, &n->l_dconv3, &n->l_dconv2, &n->l_fc, &n->l_fcd, &n->l_wconv3, &n->l_wconv2};
+  for (int i = 0; i < 8 && rc == DZ_OK; ++i)
+    if (all[i]->nctas > 0) rc = n->plan.localize_maps(*all[i]);
   if (rc == DZ_OK) rc = n->plan.upload();
   if (rc == DZ_OK) rc = UmPlan::configure();
   if (rc != DZ_OK) { um_net_destroy(n); return rc; }
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(conv1_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv1_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(conv1_wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       um_net_destroy(n);
       return fail(DZ_ECUDA, "conv1_umma_kernel shared memory attribute");
     }
@@ -906,15 +1310,17 @@ int um_forward_torso(UmNet* n, const uint8_t* const* const* rows, void* stream) 
     const int blob = d.pass_target[p] ? 1 : 0;
     a.rows[p] = rows[p];
     a.bias[p] = (blob ? d.target : d.online) + d.off_conv_b[0];
-    a.map_hi[p] = n->map_wf1[blob][0]; a.map_lo[p] = n->map_wf1[blob][1];
+    a.blob[p] = blob;
   }
+  for (int b = 0; b < 2; ++b)
+    for (int part = 0; part < 2; ++part) a.wmap[b][part] = n->plan.maps[n->map_wf1[b][part]];
   a.out_hi = n->act_hi[0]; a.out_lo = n->act_lo[0]; a.out_f32 = n->act_f32[0];
   a.npass = d.npass; a.B = d.B; a.W = d.W; a.oh = n->h1; a.ow = n->w1; a.m_pass = d.B * n->h1 * n->w1;
   a.tiles_per_pass = n->conv1_tiles_per_pass; a.ntiles = a.tiles_per_pass * d.npass; a.stag_bytes = n->conv1_stag_bytes;
   const size_t smem = 2048 + kC1W + kC1A + 2 * (size_t)a.stag_bytes;
   if (smem > 227 * 1024) return fail(DZ_EINVAL, "conv1 staging does not fit");
   const unsigned grid = (unsigned)std::min(148, a.ntiles);
-  DZ_LAUNCH_NAMED("conv1_fwd", conv1_umma_kernel, grid, kThreadsU, smem, stream, a, n->plan.d_maps);
+  DZ_LAUNCH_NAMED("conv1_fwd", conv1_umma_kernel, grid, kThreadsU, smem, stream, a);
   DZ_TRY_RC(n->plan.launch("conv2_fwd", n->l_conv2, stream));
   DZ_TRY_RC(n->plan.launch("conv3_fwd", n->l_conv3, stream));
   return DZ_OK;
@@ -959,6 +1365,46 @@ int um_backward_fc(UmNet* n, const float* noise, void* stream) {
 
 int um_split_dact3(UmNet* n, void* stream) {
   return um_split(n->dact_f32[2], n->dact_hi[2], n->dact_lo[2], (long long)n->d.B * n->feat, stream);
+}
+
+int um_wgrad_conv1(UmNet* n, const uint8_t* const* rows0, void* stream) {
+  const UmNetDesc& d = n->d;
+  Conv1WgArgs a;
+  memset(&a, 0, sizeof(a));
+  a.rows = rows0; a.gmap[0] = n->plan.maps[n->map_g1[0]]; a.gmap[1] = n->plan.maps[n->map_g1[1]]; a.partial = n->wg1_part;
+  a.B = d.B; a.W = d.W; a.oh = n->h1; a.ow = n->w1; a.m_pass = d.B * n->h1 * n->w1;
+  a.ntiles = (a.m_pass + 127) / 128; a.stag_bytes = n->conv1_stag_bytes;
+  const size_t smem = 2048 + kC1G + kC1A + 2 * (size_t)a.stag_bytes;
+  if (smem > 227 * 1024) return fail(DZ_EINVAL, "conv1 wgrad staging does not fit");
+  DZ_LAUNCH_NAMED("conv1_wgrad", conv1_wgrad_umma_kernel, (unsigned)n->wg1_ctas, kThreadsU, smem, stream, a);
+  return DZ_OK;
+}
+
+int um_wgrad_conv3(UmNet* n, void* stream) { return n->plan.launch("conv3_wgrad", n->l_wconv3, stream); }
+int um_wgrad_conv2(UmNet* n, void* stream) { return n->plan.launch("conv2_wgrad", n->l_wconv2, stream); }
+
+// dW / db of conv3 and conv2 from the split partials (+ optionally conv1's FMA partials in the same launch).
+int um_wgrad_finish(UmNet* n, float* dW3, float* db3, float* dW2, float* db2, const float* c1_partial, int c1_splits, float* dW1,
+                    float* db1, void* stream) {
+  WgFinishBatch b;
+  memset(&b, 0, sizeof(b));
+  float* sc = n->wg_scratch;
+  b.f[0] = WgFinish{n->wg3_part, n->wg3_splits, 576 * 64, 576 * 64, dW3, n->dact_f32[2], n->d.B * n->h3 * n->w3, 64, db3, sc, n->wg_ticket};
+  b.f[1] = WgFinish{n->wg2_part, n->wg2_splits, 512 * 64, 512 * 64, dW2, n->dact_f32[1], n->d.B * n->h2 * n->w2, 64, db2, sc + 256 * 64, n->wg_ticket + 1};
+  b.n = 2;
+  if (c1_partial) {   // conv1 partials of the FMA kernel: [splits][256 + 1 (bias row)][32]; the bias is recomputed here from dact1
+    b.f[2] = WgFinish{c1_partial, c1_splits, 257 * 32, 256 * 32, dW1, n->dact_f32[0], n->d.B * n->h1 * n->w1, 32, db1, sc + 2 * 256 * 64, n->wg_ticket + 2};
+    b.n = 3;
+  } else if (dW1) {   // conv1 partials of conv1_wgrad_umma_kernel: one [256][32] per CTA
+    b.f[2] = WgFinish{n->wg1_part, n->wg1_ctas, 256 * 32, 256 * 32, dW1, n->dact_f32[0], n->d.B * n->h1 * n->w1, 32, db1, sc + 2 * 256 * 64, n->wg_ticket + 2};
+    b.n = 3;
+  }
+  int max_chunks = 1;
+  for (int q = 0; q < b.n; ++q) max_chunks = std::max(max_chunks, (b.f[q].M + kWgChunkRows - 1) / kWgChunkRows);
+  if (max_chunks > kWgMaxChunks) return fail(DZ_EINVAL, "bias-gradient reduction: too many row chunks");
+  dim3 grid((unsigned)(kWgSumBlocks + max_chunks), (unsigned)b.n);
+  DZ_LAUNCH_NAMED("wgrad_finish", um_wgrad_finish_kernel, grid, 256, 0, stream, b);
+  return DZ_OK;
 }
 
 int um_backward_conv3(UmNet* n, void* stream) { return n->plan.launch("conv3_dgrad", n->l_dconv3, stream); }

@@ -44,6 +44,11 @@ int um_forward_fc(UmNet* n, const float* noise, void* stream);                 /
 int um_split_dh1(UmNet* n, void* stream);                                      // dh1 fp32 -> hi/lo (if the producer wrote fp32 only)
 int um_backward_fc(UmNet* n, const float* noise, void* stream);                // fc1 / noisy1 input gradient + finish -> dact3
 int um_split_dact3(UmNet* n, void* stream);                                    // dact3 fp32 -> hi/lo (IQN: produced by the Hadamard kernel)
+int um_wgrad_conv1(UmNet* n, const uint8_t* const* rows0, void* stream);       // uint8 rows x dact1 -> one partial per CTA
+int um_wgrad_conv3(UmNet* n, void* stream);                                    // act2 x dact3 -> split partials
+int um_wgrad_conv2(UmNet* n, void* stream);                                    // act1 x dact2 -> split partials
+int um_wgrad_finish(UmNet* n, float* dW3, float* db3, float* dW2, float* db2, const float* c1_partial, int c1_splits, float* dW1,
+                    float* db1, void* stream);                                 // partial sums + bias gradients, one launch
 int um_backward_conv3(UmNet* n, void* stream);                                 // dact3 -> dact2
 int um_backward_conv2(UmNet* n, void* stream);                                 // dact2 -> dact1
 
