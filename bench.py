@@ -62,6 +62,17 @@ def workload_name(args):
   return '%s_%s_nstep%d_cap%d_b%d_84x84x4' % (args.agent, rep, n, args.capacity, args.batch)
 
 
+def config_of(args, target_period):
+  """The workload description; identical for `--impl ours` and `--impl reference` (the driver compares them)."""
+  return {'workload': workload_name(args), 'agent': args.agent, 'replay_capacity': args.capacity, 'batch': args.batch,
+          'replay_bytes_per_gpu': int(args.capacity) * 2 * 84 * 84 * 4, 'obs': '84x84x4 uint8',
+          'target_sync_period_steps': target_period,
+          'l2': 'inputs larger than L2: 56.4 GB replay store sampled at random rows; parameters+optimizer state as in '
+                'steady-state training',
+          'multi_gpu': 'independent replay+learner shard per rank; the target refresh is an NCCL broadcast of the online blob',
+          'seed': args.seed}
+
+
 class ClockSampler:
   """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
 
@@ -111,25 +122,36 @@ def measured_peaks():
   return 6650.0, 1590.0, 'fallback (B200_PROFILING.md)'
 
 
+def host_cores():
+  try:
+    return len(os.sched_getaffinity(0))
+  except Exception:
+    return os.cpu_count() or 1
+
+
 def reference_arm(args, rank, world):
-  """The oracle PORT of the reference algorithm on the host cores (rank 0 only)."""
+  """The oracle PORT of the reference algorithm on the host cores (rank 0 only; the other ranks exit without work).
+  torchrun exports OMP_NUM_THREADS=1, so the thread count is set explicitly to every core this process may use, and
+  reported.  Ten untimed pre-warm steps (thread pools, allocator) come before the W warm-up + K timed steps."""
   if rank != 0:
     return
   from oracle import cpu_reference
-  steps = max(1, args.steps)
-  res = cpu_reference.run(args.agent, capacity=args.capacity, batch=args.batch, steps=steps, warmup=min(args.warmup, 3),
-                          seed=args.seed, budget_s=120.0)
+  cores = host_cores()
+  steps, warmup = max(1, args.steps), max(0, args.warmup)
+  res = cpu_reference.run(args.agent, capacity=args.capacity, batch=args.batch, steps=steps, warmup=warmup, seed=args.seed,
+                          threads=cores, prewarm=10, budget_s=150.0)
   value = res['steps_per_s']
-  sample = ('%d learner steps (replay.sample + update + update_priorities) of %s; replay %.2f ms + learner %.2f ms per '
-            'step; observations reference a pool of 512 synthetic frames' % (res['steps'], workload_name(args),
-                                                                             res['replay_ms'], res['learner_ms']))
+  sample = ('%d learner steps (replay.sample + update + update_priorities) of %s after %d warm-up (+10 pre-warm) steps; replay '
+            '%.2f ms + learner %.2f ms per step; observations reference a pool of 512 synthetic frames'
+            % (res['steps'], workload_name(args), warmup, res['replay_ms'], res['learner_ms']))
   line = {
       'impl': 'reference', 'metric': 'learner_grad_steps_per_sec', 'value': value, 'unit': 'grad-steps/s',
       'sampled_transitions_per_sec': value * args.batch, 'n_gpus': args.gpus, 'steps': res['steps'],
-      'warmup': min(args.warmup, 3), 'ms_per_step': 1e3 / value, 'higher_is_better': True, 'scaling': 'weak',
-      'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-      'config': {'workload': workload_name(args), 'note': 'oracle port (numpy replay + torch-CPU float32 learner); JAX CPU '
-                 'path not installable'},
+      'warmup': warmup, 'ms_per_step': 1e3 / value, 'higher_is_better': True, 'scaling': 'weak',
+      'vs_baseline': None, 'dtype': 'f32 (f64 sum tree)', 'data': 'synthetic',
+      'config': config_of(args, AGENT_SETUP[args.agent][3]),
+      'impl_note': 'oracle port (numpy replay, one thread as the reference; torch-CPU float32 learner on all host cores); the '
+                   'JAX CPU path is not installable here or on the GPU box',
       'cpu_baseline': {'value': value, 'unit': 'grad-steps/s', 'cores': res['cores'], 'kind': 'port', 'sample': sample},
       'e2e': {'value': value, 'unit': 'grad-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
       'gpu_launches': 0,

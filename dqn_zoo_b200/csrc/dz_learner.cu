@@ -2155,7 +2155,7 @@ int run_optimizer(dz_learner* l, float* user_norm, bool apply, void* stream) {
 struct WriteBack { const dz_replay_view* view; const int64_t* indices; const float* priorities; double alpha; };
 
 int update_impl(dz_learner* l, const dz_batch* batch, const dz_update_outputs* out, int apply_update, float* max_seen,
-                const WriteBack* wb, void* stream) {
+                const WriteBack* wb, void* stream, bool weights_packed = false) {
   const dz_learner_config& c = l->cfg;
   const Dims& d = l->d;
   const int B = l->B;
@@ -2177,7 +2177,8 @@ int update_impl(dz_learner* l, const dz_batch* batch, const dz_update_outputs* o
     if (nj != l->um_npass) return fail(DZ_EINVAL, "tcgen05 path: pass count mismatch");
     const uint8_t* const* rows[3] = {nullptr, nullptr, nullptr};
     for (int i = 0; i < nj; ++i) rows[i] = jobs[i].rows;
-    DZ_TRY(um_pack_weights(l->um, stream));
+    if (weights_packed) DZ_TRY(join_side(l, stream));   // packed on the side stream, concurrently with the sampler
+    else DZ_TRY(um_pack_weights(l->um, stream));
     DZ_TRY(um_forward_torso(l->um, rows, stream));
     if (c.kind != DZ_IQN) DZ_TRY(um_forward_fc(l->um, batch->d_noise, stream));
   } else {
@@ -2362,6 +2363,9 @@ int dz_learner_learn(dz_learner* l, const dz_replay_view* replay, int32_t priori
   const int B = l->B;
   BatchExtras ex{l->rows_sample[0], l->rows_sample[1], l->s_a, l->s_r, l->s_d, prioritized ? l->s_w : nullptr, 1};
   if (replay->obs_bytes != (int64_t)l->d.H * l->d.W * l->d.C) return fail(DZ_EINVAL, "replay observation size does not match the network");
+  // conv weight images do not depend on the sampled batch: pack them on the side stream while the sampler runs
+  const bool pack_aside = l->um != nullptr && l->side != nullptr;
+  if (pack_aside) DZ_TRY(um_pack_weights(l->um, fork_side(l, stream)));
   DZ_TRY(launch_sample(replay, prioritized, &io->sample_in, &io->sample_out, B, ex, stream));
   dz_batch batch;
   batch.d_s_tm1_rows = l->rows_sample[0];
@@ -2371,7 +2375,7 @@ int dz_learner_learn(dz_learner* l, const dz_replay_view* replay, int32_t priori
   batch.d_taus = io->d_taus; batch.d_noise = io->d_noise;
   WriteBack wb{replay, io->sample_out.d_indices, io->update_out.d_priorities, io->priority_exponent};
   if (prioritized && !io->update_out.d_priorities) return fail(DZ_EINVAL, "prioritized learn needs update_out.d_priorities");
-  DZ_TRY(update_impl(l, &batch, &io->update_out, 1, io->d_max_seen_priority, prioritized ? &wb : nullptr, stream));
+  DZ_TRY(update_impl(l, &batch, &io->update_out, 1, io->d_max_seen_priority, prioritized ? &wb : nullptr, stream, pack_aside));
   return DZ_OK;
 }
 
@@ -2417,6 +2421,14 @@ int dz_learner_q_values(dz_learner* l, const uint8_t* d_obs, const float* d_taus
 int dz_learner_sync_target(dz_learner* l, void* stream) {
   DZ_CUDA_OK(cudaMemcpyAsync(l->buf.d_target, l->buf.d_online, l->lay.total * sizeof(float), cudaMemcpyDeviceToDevice,
                              (cudaStream_t)stream));
+  return DZ_OK;
+}
+
+// Debug hook: the tcgen05 launch named `tag` ("conv2_fwd", "conv3_fwd", "fc1_fwd", "fc1_dgrad", "conv3_dgrad", "conv2_dgrad",
+// "conv3_wgrad", "conv2_wgrad") writes the clock stamps of its CTA 0 into d_trace (512 int64); nullptr switches it off.
+int dz_test_learner_trace(dz_learner* l, const char* tag, long long* d_trace) {
+  if (!l->um) return fail(DZ_EINVAL, "the tcgen05 path is not active for this learner");
+  um_net_trace(l->um, tag, d_trace);
   return DZ_OK;
 }
 

@@ -109,7 +109,7 @@ int UmPlan::configure() {
   return DZ_OK;
 }
 
-int UmPlan::launch(const char* tag, const UmLaunch& l, void* stream) const {
+int UmPlan::launch(const char* tag, const UmLaunch& l, void* stream, long long* d_trace) const {
   if (l.nctas <= 0) return DZ_OK;
   if (!d_ctas) return fail(DZ_EINVAL, "umma plan not uploaded");
   if (l.stages < 1 || l.stages > um::kStagesMax || l.stage_bytes % 1024) return fail(DZ_EINVAL, "umma launch geometry");
@@ -123,10 +123,10 @@ int UmPlan::launch(const char* tag, const UmLaunch& l, void* stream) const {
   for (int q = l.nmaps; q < um::kMaxMapsPerLaunch; ++q) lm.m[q] = maps[l.map_ids[0]];
   if (v == 0)
     DZ_LAUNCH_NAMED(tag, um::umma_gemm_kernel<32>, (unsigned)l.nctas, um::kThreadsU, smem, stream, lm, d_ctas + l.cta0, d_probs, d_ops, l.nmaps, l.stages,
-                    l.stage_bytes);
+                    l.stage_bytes, d_trace);
   else
     DZ_LAUNCH_NAMED(tag, um::umma_gemm_kernel<64>, (unsigned)l.nctas, um::kThreadsU, smem, stream, lm, d_ctas + l.cta0, d_probs, d_ops, l.nmaps, l.stages,
-                    l.stage_bytes);
+                    l.stage_bytes, d_trace);
   return DZ_OK;
 }
 

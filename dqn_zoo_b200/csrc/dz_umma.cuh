@@ -180,12 +180,13 @@ constexpr int kCtlBytes = 1024 + 1024 + kMaxOpsPerCta * 32;   // barriers | prob
 template <int NJT>
 __global__ void __launch_bounds__(kThreadsU, 1)
     umma_gemm_kernel(const __grid_constant__ UmMaps maps, const UmCta* __restrict__ ctas, const UmProblem* __restrict__ probs,
-                     const UmTmaOp* __restrict__ ops, int nmaps, int stages, uint32_t stage_bytes) {
+                     const UmTmaOp* __restrict__ ops, int nmaps, int stages, uint32_t stage_bytes, long long* __restrict__ trace) {
   if (threadIdx.x < nmaps) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.m[threadIdx.x])) : "memory");
   dz::pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[323] = clock64();                               // after griddepcontrol.wait
   const UmCta cta = ctas[blockIdx.x];
   const int ST = stages;
   const int nst = (int)cta.nstages;
@@ -230,6 +231,7 @@ __global__ void __launch_bounds__(kThreadsU, 1)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[324] = clock64();                               // setup done
   const UmProblem& p = *p_smem;
   const int run_stages = (int)p.run_stages;
   const int nruns = (nst + run_stages - 1) / run_stages;
@@ -253,6 +255,7 @@ __global__ void __launch_bounds__(kThreadsU, 1)
         const uint32_t dst = smem_u32(stage_base + (size_t)s * stage_bytes) + op.smem_off;
         tma_load_5d(dst, &maps.m[op.map], &full[s], op.c[0], op.c[1], op.c[2], op.c[3], op.c[4]);
       }
+      if (trace && blockIdx.x == 0 && lane == 0 && it < 64) trace[it] = clock64();                 // [0,64): TMA issued
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -276,6 +279,7 @@ __global__ void __launch_bounds__(kThreadsU, 1)
       }
       mbar_wait(any_conv ? &ready[s] : &full[s], ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (trace && blockIdx.x == 0 && lane == 0 && it < 64) trace[64 + it] = clock64();            // [64,128): stage data ready
       if (lane == 0) {
         const uint32_t st = smem_u32(stage_base + (size_t)s * stage_bytes);
         const uint32_t a_hi = st, a_lo = st + a_pb, b_hi = st + a_bytes, b_lo = b_hi + b_pb;
@@ -290,6 +294,7 @@ __global__ void __launch_bounds__(kThreadsU, 1)
         }
         mma_commit(&empty[s]);
         if (in_run == run_stages - 1 || it == nst - 1) mma_commit(&acc_full[buf]);
+        if (trace && blockIdx.x == 0 && it < 64) trace[128 + it] = clock64();                      // [128,192): MMAs issued
       }
       __syncwarp();
     }
@@ -303,6 +308,7 @@ __global__ void __launch_bounds__(kThreadsU, 1)
       const int buf = run & 1;
       mbar_wait(&acc_full[buf], ((uint32_t)run >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (trace && blockIdx.x == 0 && warp == 2 && lane == 0 && run < 64) trace[192 + run] = clock64();   // [192,256): accumulator ready
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * NJT);
 #pragma unroll
       for (int c0 = 0; c0 < NJT; c0 += 32) {
@@ -315,8 +321,10 @@ __global__ void __launch_bounds__(kThreadsU, 1)
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (trace && blockIdx.x == 0 && warp == 2 && lane == 0 && run < 64) trace[256 + run] = clock64();   // [256,320): run drained
     }
     const int r = quarter * 32 + lane;
+    if (trace && blockIdx.x == 0 && warp == 2 && lane == 0) trace[320] = clock64();                       // epilogue math starts
     if (p.epi == UM_EPI_PARTIAL) {
       const int i = cta.i0 + r;
       if (i < p.MI) {
@@ -380,11 +388,13 @@ __global__ void __launch_bounds__(kThreadsU, 1)
       if (lane == 0) mbar_arrive(&ready[s]);
     }
   }
+  if (trace && blockIdx.x == 0 && warp == 2 && lane == 0) trace[321] = clock64();                         // epilogue stores issued
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
+  if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[322] = clock64();
 }
 
 }  // namespace um

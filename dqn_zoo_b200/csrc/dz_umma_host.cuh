@@ -37,7 +37,7 @@ struct UmPlan {
   int localize_maps(UmLaunch& l);
   int upload();          // (re)allocates and copies all four tables
   void release();
-  int launch(const char* tag, const UmLaunch& l, void* stream) const;
+  int launch(const char* tag, const UmLaunch& l, void* stream, long long* d_trace = nullptr) const;   // d_trace: 512 clock stamps of CTA 0 (debug)
   static int configure();   // one-time kernel attributes (outside any stream capture)
 };
 

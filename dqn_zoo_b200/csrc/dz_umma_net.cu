@@ -39,6 +39,9 @@ struct UmNet {
   struct Patch { int prob; int field; int64_t off; };   // field 0: A.scale_r, 1: scale_i
   std::vector<Patch> patches;
   const float* noise_cached = nullptr;
+  std::string trace_tag;                   // debug: the launch with this tag writes CTA 0's clock stamps to trace_ptr
+  long long* trace_ptr = nullptr;
+  long long* tr(const char* tag) const { return trace_ptr && trace_tag == tag ? trace_ptr : nullptr; }
 };
 
 namespace {
@@ -1275,6 +1278,8 @@ int um_net_create(const UmNetDesc& d, char* base, UmNet** out) {
   return DZ_OK;
 }
 
+void um_net_trace(UmNet* n, const char* tag, long long* d_trace) { n->trace_tag = tag ? tag : ""; n->trace_ptr = d_trace; }
+
 void um_net_destroy(UmNet* n) {
   if (!n) return;
   n->plan.release();
@@ -1321,8 +1326,8 @@ int um_forward_torso(UmNet* n, const uint8_t* const* const* rows, void* stream) 
   if (smem > 227 * 1024) return fail(DZ_EINVAL, "conv1 staging does not fit");
   const unsigned grid = (unsigned)std::min(148, a.ntiles);
   DZ_LAUNCH_NAMED("conv1_fwd", conv1_umma_kernel, grid, kThreadsU, smem, stream, a);
-  DZ_TRY_RC(n->plan.launch("conv2_fwd", n->l_conv2, stream));
-  DZ_TRY_RC(n->plan.launch("conv3_fwd", n->l_conv3, stream));
+  DZ_TRY_RC(n->plan.launch("conv2_fwd", n->l_conv2, stream, n->tr("conv2_fwd")));
+  DZ_TRY_RC(n->plan.launch("conv3_fwd", n->l_conv3, stream, n->tr("conv3_fwd")));
   return DZ_OK;
 }
 
@@ -1330,7 +1335,7 @@ int um_forward_fc(UmNet* n, const float* noise, void* stream) {
   const UmNetDesc& d = n->d;
   if (!d.use_fc) return fail(DZ_EINVAL, "fc layers are not on the tcgen05 path for this agent");
   if (d.noisy) DZ_TRY_RC(apply_noise(n, noise, stream));
-  DZ_TRY_RC(n->plan.launch(d.noisy ? "noisy1_fwd" : "fc1_fwd", n->l_fc, stream));
+  DZ_TRY_RC(n->plan.launch(d.noisy ? "noisy1_fwd" : "fc1_fwd", n->l_fc, stream, n->tr("fc1_fwd")));
   FcFinishArgs a;
   memset(&a, 0, sizeof(a));
   a.part = n->fc_part; a.S = n->fc_splits; a.B = d.B; a.nstream = d.nstream; a.noisy = d.noisy; a.npass = d.npass; a.h1 = n->h1_buf;
@@ -1356,7 +1361,7 @@ int um_backward_fc(UmNet* n, const float* noise, void* stream) {
   const UmNetDesc& d = n->d;
   if (!d.use_fc) return fail(DZ_EINVAL, "fc layers are not on the tcgen05 path for this agent");
   if (d.noisy) DZ_TRY_RC(apply_noise(n, noise, stream));
-  DZ_TRY_RC(n->plan.launch(d.noisy ? "noisy1_dgrad" : "fc1_dgrad", n->l_fcd, stream));
+  DZ_TRY_RC(n->plan.launch(d.noisy ? "noisy1_dgrad" : "fc1_dgrad", n->l_fcd, stream, n->tr("fc1_dgrad")));
   const long long total = (long long)d.B * n->feat;
   DZ_LAUNCH_NAMED("fcd_finish", um_fcd_finish_kernel, (unsigned)std::min<long long>(ceil_div(total / 4, 256), 148 * 4), 256, 0, stream,
                   n->fcd_part, n->fcd_nsrc * n->fcd_splits, total, n->act_hi[2], n->dact_f32[2], n->dact_hi[2], n->dact_lo[2], total / 4);
@@ -1380,8 +1385,8 @@ int um_wgrad_conv1(UmNet* n, const uint8_t* const* rows0, void* stream) {
   return DZ_OK;
 }
 
-int um_wgrad_conv3(UmNet* n, void* stream) { return n->plan.launch("conv3_wgrad", n->l_wconv3, stream); }
-int um_wgrad_conv2(UmNet* n, void* stream) { return n->plan.launch("conv2_wgrad", n->l_wconv2, stream); }
+int um_wgrad_conv3(UmNet* n, void* stream) { return n->plan.launch("conv3_wgrad", n->l_wconv3, stream, n->tr("conv3_wgrad")); }
+int um_wgrad_conv2(UmNet* n, void* stream) { return n->plan.launch("conv2_wgrad", n->l_wconv2, stream, n->tr("conv2_wgrad")); }
 
 // dW / db of conv3 and conv2 from the split partials (+ optionally conv1's FMA partials in the same launch).
 int um_wgrad_finish(UmNet* n, float* dW3, float* db3, float* dW2, float* db2, const float* c1_partial, int c1_splits, float* dW1,
@@ -1407,7 +1412,7 @@ int um_wgrad_finish(UmNet* n, float* dW3, float* db3, float* dW2, float* db2, co
   return DZ_OK;
 }
 
-int um_backward_conv3(UmNet* n, void* stream) { return n->plan.launch("conv3_dgrad", n->l_dconv3, stream); }
-int um_backward_conv2(UmNet* n, void* stream) { return n->plan.launch("conv2_dgrad", n->l_dconv2, stream); }
+int um_backward_conv3(UmNet* n, void* stream) { return n->plan.launch("conv3_dgrad", n->l_dconv3, stream, n->tr("conv3_dgrad")); }
+int um_backward_conv2(UmNet* n, void* stream) { return n->plan.launch("conv2_dgrad", n->l_dconv2, stream, n->tr("conv2_dgrad")); }
 
 }  // namespace dz

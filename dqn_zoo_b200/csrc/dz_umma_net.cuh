@@ -30,6 +30,7 @@ int64_t um_net_workspace_bytes(const UmNetDesc& d);
 // `base` may be nullptr (size query through carve); buffers are carved from it in a fixed order.
 int um_net_create(const UmNetDesc& d, char* base, UmNet** out);
 void um_net_destroy(UmNet* n);
+void um_net_trace(UmNet* n, const char* tag, long long* d_trace);   // debug: clock stamps of CTA 0 of the launch `tag`
 
 // Buffers the rest of the learner reads / writes (fp32 views of the activations and gradients).
 float* um_act_f32(UmNet* n, int layer, int pass);      // layer 1..3 -> [B][h][w][C]

@@ -344,6 +344,8 @@ int dz_test_threefry2x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uin
  * tests/tools only. */
 int dz_test_learner_buffer(dz_learner* l, const char* name, float** d_ptr, int64_t* count);
 int dz_test_copy(void* d_dst, const void* d_src, int64_t bytes, void* stream);   /* device-to-device, tests only */
+/* Debug: the tcgen05 launch named `tag` writes the clock stamps of its CTA 0 into d_trace (512 int64). */
+int dz_test_learner_trace(dz_learner* l, const char* tag, long long* d_trace);
 int64_t dz_test_tc_pgemm_work(int32_t a_rows, int32_t b_rows, int32_t red);
 int dz_test_tc_pgemm(const float* d_A, int32_t a_rows, int32_t a_ld, int32_t a_red_contig, const float* d_B,
                      int32_t b_rows, int32_t b_ld, int32_t b_red_contig, int32_t red, int32_t a_ones_row,

@@ -68,7 +68,7 @@ def _scalars(seed, rows, num_actions):
   return None, np.concatenate(out_a), np.concatenate(out_r), np.concatenate(out_d)
 
 
-def run(kind='rainbow', capacity=1000000, batch=32, steps=20, warmup=3, seed=1, threads=None, budget_s=60.0):
+def run(kind='rainbow', capacity=1000000, batch=32, steps=20, warmup=3, seed=1, threads=None, budget_s=60.0, prewarm=0):
   """Returns dict(steps_per_s, replay_ms, learner_ms, steps, cores)."""
   if threads:
     torch.set_num_threads(threads)
@@ -80,6 +80,7 @@ def run(kind='rainbow', capacity=1000000, batch=32, steps=20, warmup=3, seed=1, 
   t_replay = t_learn = 0.0
   done = 0
   t_begin = None
+  warmup = warmup + prewarm   # pre-warm steps are untimed like the warm-up, but not part of the reported warm-up count
   for it in range(warmup + steps):
     if it == warmup:
       t_replay = t_learn = 0.0
