@@ -33,6 +33,7 @@ inline int fail(int code, const char* fmt, const char* a = "", const char* b = "
 // dominant kernel on its own stream.  Off in every timed run.
 extern bool g_profile;
 void profile_mark(const char* name, void* stream, bool begin);
+void profile_geometry(unsigned gx, unsigned gy, unsigned bx);   // launch geometry of the record opened by profile_mark
 
 // Programmatic dependent launch (PDL).  Every kernel of this library begins with pdl_enter() = griddepcontrol.wait
 // and is launched with the programmatic-stream-serialization attribute: the next kernel's launch and block
@@ -42,12 +43,38 @@ void profile_mark(const char* name, void* stream, bool begin);
 // the dependents EARLY (griddepcontrol.launch_dependents at kernel entry, -DDZ_PDL_EARLY) was slower (dqn 265 us):
 // the early CTAs spin at their wait and take issue slots and SM space from the kernel that is still running.
 // DZ_NO_PDL=1 launches with full serialization.
+// Debug timeline (dz_debug_timeline): when a buffer is installed, thread 0 of block 0 of EVERY kernel appends
+// (globaltimer, gridDim.x << 32 | gridDim.y << 16 | blockDim.x) right after its griddepcontrol.wait, i.e. at the moment
+// everything it depends on has completed.  Read back after a CUDA-graph replay this is the true timeline of the step
+// (launch gaps included), which neither per-launch events (eager only) nor ncu (serialised) can show.  Each translation
+// unit has its own copy of the pointer (no relocatable device code); TimelineRegistrar collects the setters.
+static __device__ unsigned long long* g_timeline = nullptr;
+__device__ __forceinline__ void timeline_stamp() {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    unsigned long long* tl = g_timeline;
+    if (tl != nullptr) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      const unsigned int idx = atomicAdd(reinterpret_cast<unsigned int*>(tl), 1u);
+      if (idx < 4000u) {
+        tl[2 + 2 * idx] = t;
+        tl[3 + 2 * idx] = ((unsigned long long)gridDim.x << 32) | ((unsigned long long)gridDim.y << 16) | blockDim.x;
+      }
+    }
+  }
+}
 __device__ __forceinline__ void pdl_enter() {
 #ifdef DZ_PDL_EARLY
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  timeline_stamp();
 }
+typedef int (*timeline_setter_t)(unsigned long long*);
+void timeline_register(timeline_setter_t fn);      // dz_replay.cu
+static int timeline_set_this_tu(unsigned long long* p) { return (int)cudaMemcpyToSymbol(g_timeline, &p, sizeof(p)); }
+struct TimelineRegistrar { TimelineRegistrar() { timeline_register(timeline_set_this_tu); } };
+static TimelineRegistrar g_timeline_registrar;
 extern int g_pdl;   // -1 = read DZ_NO_PDL on first use
 extern int g_carveout;   // -1 = read DZ_CARVEOUT on first use; > 0: preferred shared-memory carveout (percent) for EVERY kernel
 
@@ -77,7 +104,7 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
 // Every kernel launch goes through this so bench.py can report `gpu_launches`.
 #define DZ_LAUNCH_NAMED(name, kernel, grid, block, smem, stream, ...)                        \
   do {                                                                                       \
-    if (dz::g_profile) dz::profile_mark(name, stream, true);                                 \
+    if (dz::g_profile) { dz::profile_mark(name, stream, true); dim3 _g(grid), _b(block); dz::profile_geometry(_g.x, _g.y, _b.x); } \
     dz::launch_kernel(kernel, dim3(grid), dim3(block), (size_t)(smem), (cudaStream_t)(stream), __VA_ARGS__); \
     if (dz::g_profile) dz::profile_mark(name, stream, false);                                \
     dz::g_launches.fetch_add(1, std::memory_order_relaxed);                                  \

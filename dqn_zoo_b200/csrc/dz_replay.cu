@@ -12,18 +12,24 @@ namespace dz {
 
 thread_local std::string g_last_error;
 std::atomic<int64_t> g_launches{0};
+std::vector<timeline_setter_t>& timeline_setters() { static std::vector<timeline_setter_t> v; return v; }
+void timeline_register(timeline_setter_t fn) { timeline_setters().push_back(fn); }
 int g_pdl = -1;
 int g_carveout = -1;
 bool g_profile = false;
 
 namespace {
-struct ProfileRec { const char* name; cudaEvent_t a, b; };
+struct ProfileRec { const char* name; cudaEvent_t a, b; unsigned gx, gy, bx; };
 std::vector<ProfileRec> g_profile_recs;
 }  // namespace
 
+void profile_geometry(unsigned gx, unsigned gy, unsigned bx) {
+  if (!g_profile_recs.empty()) { g_profile_recs.back().gx = gx; g_profile_recs.back().gy = gy; g_profile_recs.back().bx = bx; }
+}
+
 void profile_mark(const char* name, void* stream, bool begin) {
   if (begin) {
-    ProfileRec r{name, nullptr, nullptr};
+    ProfileRec r{name, nullptr, nullptr, 0, 0, 0};
     cudaEventCreate(&r.a);
     cudaEventCreate(&r.b);
     cudaEventRecord(r.a, (cudaStream_t)stream);
@@ -531,6 +537,15 @@ const char* dz_last_error(void) { return g_last_error.c_str(); }
 const char* dz_build_info(void) { return "dqn_zoo_b200 0.1 sm_100a " __DATE__ " " __TIME__; }
 int64_t dz_launch_count(void) { return g_launches.load(); }
 
+// Debug: installs (or, with nullptr, removes) the device buffer every kernel of the library stamps at its start
+// (dz_common.cuh: timeline_stamp).  d_buf: >= 2 + 2 * 4000 uint64, zero-initialised by the caller.
+int dz_debug_timeline(unsigned long long* d_buf) {
+  DZ_CUDA_OK(cudaDeviceSynchronize());
+  for (auto fn : timeline_setters())
+    if (fn(d_buf) != 0) return fail(DZ_ECUDA, "dz_debug_timeline: cudaMemcpyToSymbol failed");
+  return DZ_OK;
+}
+
 int dz_profile_begin(void) {
   g_profile_recs.clear();
   g_profile = true;
@@ -541,8 +556,10 @@ int dz_profile_end(char* out, int64_t cap) {
   g_profile = false;
   DZ_CUDA_OK(cudaDeviceSynchronize());
   std::map<std::string, std::pair<int64_t, double>> agg;
+  std::map<std::string, ProfileRec> geo;
   std::vector<std::string> order;
   for (auto& r : g_profile_recs) {
+    geo[r.name] = r;
     float ms = 0.f;
     cudaEventElapsedTime(&ms, r.a, r.b);
     cudaEventDestroy(r.a);
@@ -555,8 +572,8 @@ int dz_profile_end(char* out, int64_t cap) {
   std::string js = "{";
   for (size_t i = 0; i < order.size(); ++i) {
     char buf[256];
-    snprintf(buf, sizeof(buf), "%s\"%s\": [%lld, %.6f]", i ? ", " : "", order[i].c_str(), (long long)agg[order[i]].first,
-             agg[order[i]].second);
+    snprintf(buf, sizeof(buf), "%s\"%s\": [%lld, %.6f, %u, %u, %u]", i ? ", " : "", order[i].c_str(), (long long)agg[order[i]].first,
+             agg[order[i]].second, geo[order[i]].gx, geo[order[i]].gy, geo[order[i]].bx);
     js += buf;
   }
   js += "}";

@@ -113,8 +113,11 @@ int UmPlan::launch(const char* tag, const UmLaunch& l, void* stream, long long* 
   if (l.nctas <= 0) return DZ_OK;
   if (!d_ctas) return fail(DZ_EINVAL, "umma plan not uploaded");
   if (l.stages < 1 || l.stages > um::kStagesMax || l.stage_bytes % 1024) return fail(DZ_EINVAL, "umma launch geometry");
+  for (int ci = l.cta0; ci < l.cta0 + l.nctas; ++ci)
+    if (ctas[ci].ops_per_stage > 32) return fail(DZ_EINVAL, "umma launch: more than 32 TMA ops per stage");
   const size_t smem = 1024 + um::kCtlBytes + (size_t)l.stages * l.stage_bytes;
   if (smem > 227 * 1024) return fail(DZ_EINVAL, "umma launch needs too much shared memory");
+  if ((size_t)l.stages * l.stage_bytes < (size_t)128 * l.njt * 4) return fail(DZ_EINVAL, "umma launch: stage buffers smaller than the store-phase staging tile");
   const int v = l.njt == 32 ? 0 : 1;
   if (l.njt != 32 && l.njt != 64) return fail(DZ_EINVAL, "umma launch: NJT must be 32 or 64");
   DZ_TRY_CFG(configure());

@@ -92,6 +92,15 @@ constexpr int kStagesMax = 8;
 constexpr int kConvWarps = 8;
 constexpr int kThreadsU = (2 + 4 + kConvWarps) * 32;   // producer, mma, 4 epilogue, 8 converter warps
 
+// One lane of a converged warp.  With elect.sync ptxas knows that exactly one thread runs the guarded region and
+// emits the tcgen05.mma / TMA instructions back to back; under `if (lane == 0)` it wraps EVERY such instruction in an
+// ELECT / BRA.U.ANY loop over the possibly-active lanes (measured: ~75 cycles per MMA instead of the pipe's 16-32).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred P;\n elect.sync _|P, 0xffffffff;\n selp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -176,17 +185,31 @@ struct UmMaps { CUtensorMap m[kMaxMapsPerLaunch]; };   // passed as a __grid_con
 constexpr int kMaxOpsPerCta = 256;     // TMA ops of one CTA staged in shared memory (8 KB)
 constexpr int kCtlBytes = 1024 + 1024 + kMaxOpsPerCta * 32;   // barriers | problem copy | op table
 
+// Named barrier over the 12 non-producer/non-MMA warps (epilogue + converter warps): the cooperative store phase.
+__device__ __forceinline__ void bar_sync_coop() { asm volatile("bar.sync 1, 384;" ::: "memory"); }
+
+// Staging tile of the cooperative store phase: fp32 [128 rows][NJT], 16-byte chunks XOR-swizzled inside every 128-byte
+// group so that row-per-thread writes and chunk-per-thread reads are both bank-conflict free.
+template <int NJT>
+__device__ __forceinline__ float4* stage_chunk(uint8_t* base, int r, int c) {
+  return reinterpret_cast<float4*>(base + (size_t)r * (NJT * 4) + (size_t)(((c & ~7) | ((c ^ r) & 7)) << 4));
+}
+
 // grid = number of CTA descriptors; dynamic smem = kCtlBytes + stages * stage_bytes + 1024 (alignment slack).
+// Warp roles: 0 TMA producer | 1 MMA issuer | 2-5 accumulator drain (TMEM lane quarters) | 6-13 operand converters.
+// All twelve warps 2-13 take part in the final store phase (tile staged in shared memory, written out in full rows).
 template <int NJT>
 __global__ void __launch_bounds__(kThreadsU, 1)
     umma_gemm_kernel(const __grid_constant__ UmMaps maps, const UmCta* __restrict__ ctas, const UmProblem* __restrict__ probs,
                      const UmTmaOp* __restrict__ ops, int nmaps, int stages, uint32_t stage_bytes, long long* __restrict__ trace) {
   if (threadIdx.x < nmaps) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.m[threadIdx.x])) : "memory");
-  dz::pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[323] = clock64();                               // after griddepcontrol.wait
+  const bool tr = trace != nullptr && blockIdx.x == 0;
+  // The plan tables (CTA descriptors, problems, TMA programs) are written once at plan upload, never by a kernel of the
+  // step: the whole set-up below runs BEFORE griddepcontrol.wait, i.e. it overlaps the tail of the previous kernel
+  // whenever that kernel has triggered its dependents.
   const UmCta cta = ctas[blockIdx.x];
   const int ST = stages;
   const int nst = (int)cta.nstages;
@@ -231,47 +254,62 @@ __global__ void __launch_bounds__(kThreadsU, 1)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[324] = clock64();                               // setup done
+  // griddepcontrol.wait is executed per role, right before the role's first access to data an earlier kernel may have
+  // produced (the MMA warp touches only shared memory and TMEM and does not need it).
   const UmProblem& p = *p_smem;
   const int run_stages = (int)p.run_stages;
   const int nruns = (nst + run_stages - 1) / run_stages;
   const bool conv_a = p.A.convert != 0, conv_b = p.B.convert != 0;
   const bool any_conv = conv_a || conv_b;
-
   const uint32_t a_bytes = p.A.part_bytes * p.A.nparts;
+  // stores that stay row-per-lane coalesced (lane = D row, unit stride along i) are written straight from registers
+  const bool direct = p.epi == UM_EPI_PARTIAL && p.sc_i == 1;
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer: lane q issues op q of the stage
     const int nops = (int)cta.ops_per_stage;
+    int s = 0;
+    uint32_t ph = 0;
+    uint32_t st_addr = smem_u32(stage_base);
+    int oi = 0;
+    dz::pdl_enter();
+    if (tr && lane == 0) { trace[323] = clock64(); trace[324] = clock64(); }
     for (int it = 0; it < nst; ++it) {
-      const int s = it % ST;
-      const uint32_t ph = (uint32_t)(it / ST) & 1u;
       mbar_wait(&empty[s], ph ^ 1u);
+      // lane q prepares and issues op q: the operand set-up (shared-memory read, address arithmetic, moves to uniform
+      // registers) runs SIMD across the lanes and only the UTMALDG instructions themselves are serialised
+      // (measured: ~125 cycles per op; one elected thread issuing all ops in a loop: ~300 cycles per op)
       if (lane == 0) mbar_expect_tx(&full[s], cta.tx_bytes);
       __syncwarp();
       if (lane < nops) {
-        const int oi = it * nops + lane;
-        const UmTmaOp op = oi < kMaxOpsPerCta ? ops_smem[oi] : ops[cta.op0 + oi];
-        const uint32_t dst = smem_u32(stage_base + (size_t)s * stage_bytes) + op.smem_off;
-        tma_load_5d(dst, &maps.m[op.map], &full[s], op.c[0], op.c[1], op.c[2], op.c[3], op.c[4]);
+        const int o = oi + lane;
+        const UmTmaOp op = o < kMaxOpsPerCta ? ops_smem[o] : ops[cta.op0 + o];   // long programs spill to the global table
+        tma_load_5d(st_addr + op.smem_off, &maps.m[op.map], &full[s], op.c[0], op.c[1], op.c[2], op.c[3], op.c[4]);
       }
-      if (trace && blockIdx.x == 0 && lane == 0 && it < 64) trace[it] = clock64();                 // [0,64): TMA issued
+      if (tr && lane == 0 && it < 64) trace[it] = clock64();                                       // [0,64): TMA issued
+      __syncwarp();
+      oi += nops;
+      ++s; st_addr += stage_bytes;
+      if (s == ST) { s = 0; ph ^= 1u; st_addr = smem_u32(stage_base); }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
+    // Descriptors: the upper word (SBO, version, layout type) and the LBO field are loop invariants; the start-address
+    // field (bits 0-13, address >> 4 — shared memory is < 256 KB, so sums never carry out of the field) is advanced
+    // with plain adds.
     const uint32_t idesc = make_idesc(128, NJT, (int)p.A.mn_major, (int)p.B.mn_major);
-    const uint32_t a_lbo = p.A.mn_major ? p.A.lbo : 16u, b_lbo = p.B.mn_major ? p.B.lbo : 16u;
-    const uint32_t a_sbo = p.A.mn_major ? 512u : 1024u, b_sbo = p.B.mn_major ? 512u : 1024u;
-    const uint32_t a_lt = p.A.mn_major ? 1u : 2u, b_lt = p.B.mn_major ? 1u : 2u;
-    const uint32_t a_step = p.A.kstep, b_step = p.B.kstep;
-    const uint32_t a_pb = p.A.part_bytes, b_pb = p.B.part_bytes;
+    const uint32_t a_up = (p.A.mn_major ? (512u >> 4) : (1024u >> 4)) | (1u << 14) | ((p.A.mn_major ? 1u : 2u) << 29);
+    const uint32_t b_up = (p.B.mn_major ? (512u >> 4) : (1024u >> 4)) | (1u << 14) | ((p.B.mn_major ? 1u : 2u) << 29);
+    const uint32_t a_lbo = (((p.A.mn_major ? p.A.lbo : 16u) >> 4) & 0x3FFFu) << 16;
+    const uint32_t b_lbo = (((p.B.mn_major ? p.B.lbo : 16u) >> 4) & 0x3FFFu) << 16;
+    const uint32_t a_stepq = p.A.kstep >> 4, b_stepq = p.B.kstep >> 4;
+    const uint32_t a_pbq = p.A.part_bytes >> 4, b_pbq = p.B.part_bytes >> 4;
     const bool a_exact = p.A.nparts == 1, b_exact = p.B.nparts == 1;
     const int ksteps = (int)p.ksteps;
+    const uint32_t stq0 = smem_u32(stage_base) >> 4, stageq = stage_bytes >> 4, a_bytesq = a_bytes >> 4;
+    int s = 0, in_run = 0, run = 0;
+    uint32_t ph = 0, stq = stq0;
     for (int it = 0; it < nst; ++it) {
-      const int s = it % ST;
-      const uint32_t ph = (uint32_t)(it / ST) & 1u;
-      const int run = it / run_stages, in_run = it - run * run_stages;
       const int buf = run & 1;
       if (in_run == 0) {
         mbar_wait(&acc_empty[buf], (((uint32_t)run >> 1) & 1u) ^ 1u);
@@ -279,36 +317,61 @@ __global__ void __launch_bounds__(kThreadsU, 1)
       }
       mbar_wait(any_conv ? &ready[s] : &full[s], ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (trace && blockIdx.x == 0 && lane == 0 && it < 64) trace[64 + it] = clock64();            // [64,128): stage data ready
-      if (lane == 0) {
-        const uint32_t st = smem_u32(stage_base + (size_t)s * stage_bytes);
-        const uint32_t a_hi = st, a_lo = st + a_pb, b_hi = st + a_bytes, b_lo = b_hi + b_pb;
+      const bool last_of_run = in_run == run_stages - 1 || it == nst - 1;
+      if (elect_one()) {
+        if (tr && it < 64) trace[64 + it] = clock64();                                             // [64,128): stage data ready
+        uint32_t ah = a_lbo + stq, al = ah + a_pbq;
+        uint32_t bh = b_lbo + stq + a_bytesq, bl = bh + b_pbq;
         const uint32_t d = tmem_base + (uint32_t)(buf * NJT);
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t dah = make_desc_sw128(a_hi + k * a_step, a_lbo, a_sbo, a_lt), dal = make_desc_sw128(a_lo + k * a_step, a_lbo, a_sbo, a_lt);
-          const uint64_t dbh = make_desc_sw128(b_hi + k * b_step, b_lbo, b_sbo, b_lt), dbl = make_desc_sw128(b_lo + k * b_step, b_lbo, b_sbo, b_lt);
-          uint32_t acc = (in_run > 0 || k > 0) ? 1u : 0u;
+        uint32_t acc = in_run > 0 ? 1u : 0u;
+        auto kstep = [&]() {
+          const uint64_t dah = ((uint64_t)a_up << 32) | ah, dal = ((uint64_t)a_up << 32) | al;
+          const uint64_t dbh = ((uint64_t)b_up << 32) | bh, dbl = ((uint64_t)b_up << 32) | bl;
           if (!a_exact) { mma_tf32(d, dal, dbh, idesc, acc); acc = 1u; }   // small cross terms first
           if (!b_exact) { mma_tf32(d, dah, dbl, idesc, acc); acc = 1u; }
           mma_tf32(d, dah, dbh, idesc, acc);
+          acc = 1u;
+          ah += a_stepq; al += a_stepq; bh += b_stepq; bl += b_stepq;
+        };
+        if (ksteps == 4) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) kstep();
+        } else {
+          for (int k = 0; k < ksteps; ++k) kstep();
         }
         mma_commit(&empty[s]);
-        if (in_run == run_stages - 1 || it == nst - 1) mma_commit(&acc_full[buf]);
-        if (trace && blockIdx.x == 0 && it < 64) trace[128 + it] = clock64();                      // [128,192): MMAs issued
+        if (last_of_run) mma_commit(&acc_full[buf]);
+        if (it == nst - 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel's set-up overlaps our epilogue
+        if (tr && it < 64) trace[128 + it] = clock64();                                            // [128,192): MMAs issued
       }
       __syncwarp();
+      ++s; stq += stageq;
+      if (s == ST) { s = 0; ph ^= 1u; stq = stq0; }
+      if (last_of_run) { in_run = 0; ++run; } else { ++in_run; }
     }
+    if (nst == 0 && elect_one()) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   } else if (warp < 6) {
-    // ---------------------------------------------------------------- epilogue: drain runs, then write
+    // ---------------------------------------------------------------- accumulator drain
     const int quarter = warp & 3;
     float sum[NJT];
+    dz::pdl_enter();
+    if (p.epi == UM_EPI_ROWS && p.bias != nullptr) {        // the bias is the initial value of the row sums (loaded while the
+      const float* __restrict__ bias = p.bias;              // first accumulation run is still in flight)
 #pragma unroll
-    for (int t = 0; t < NJT; ++t) sum[t] = 0.f;
+      for (int t = 0; t < NJT; t += 4) {
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < p.NJ) b4 = *reinterpret_cast<const float4*>(bias + t);
+        sum[t] = b4.x; sum[t + 1] = b4.y; sum[t + 2] = b4.z; sum[t + 3] = b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < NJT; ++t) sum[t] = 0.f;
+    }
     for (int run = 0; run < nruns; ++run) {
       const int buf = run & 1;
       mbar_wait(&acc_full[buf], ((uint32_t)run >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (trace && blockIdx.x == 0 && warp == 2 && lane == 0 && run < 64) trace[192 + run] = clock64();   // [192,256): accumulator ready
+      if (tr && warp == 2 && lane == 0 && run < 64) trace[192 + run] = clock64();                  // [192,256): accumulator ready
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * NJT);
 #pragma unroll
       for (int c0 = 0; c0 < NJT; c0 += 32) {
@@ -321,14 +384,14 @@ __global__ void __launch_bounds__(kThreadsU, 1)
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
-      if (trace && blockIdx.x == 0 && warp == 2 && lane == 0 && run < 64) trace[256 + run] = clock64();   // [256,320): run drained
+      if (tr && warp == 2 && lane == 0 && run < 64) trace[256 + run] = clock64();                  // [256,320): run drained
     }
     const int r = quarter * 32 + lane;
-    if (trace && blockIdx.x == 0 && warp == 2 && lane == 0) trace[320] = clock64();                       // epilogue math starts
-    if (p.epi == UM_EPI_PARTIAL) {
+    if (tr && warp == 2 && lane == 0) trace[320] = clock64();                                       // store phase starts
+    if (direct) {
       const int i = cta.i0 + r;
       if (i < p.MI) {
-        float* dst = p.C + (long long)cta.split * p.split_stride + (long long)i * p.sc_i;
+        float* dst = p.C + (long long)cta.split * p.split_stride + i;
         const float s = p.scale_i ? p.scale_i[i] : 1.0f;
         const long long sc_j = p.sc_j;
         const int NJ = p.NJ;
@@ -337,64 +400,97 @@ __global__ void __launch_bounds__(kThreadsU, 1)
           if (t < NJ) dst[(long long)t * sc_j] = sum[t] * s;
       }
     } else {
-      const int pw = p.pw;
-      const int ro = r / pw, ri = r - ro * pw;
-      if (ro < cta.ph_valid && ri < cta.pw_valid) {
-        const long long dst = (long long)cta.row_base + (long long)ro * p.rs_outer + (long long)ri * p.rs_inner;
-        const int NJ = p.NJ;
-        const long long ld = p.out_ld;
-        const float* bias = p.bias;
-        const float* mask = p.mask ? p.mask + dst * ld : nullptr;
-        float* oh = p.out_hi ? p.out_hi + dst * ld : nullptr;
-        float* ol = p.out_lo ? p.out_lo + dst * ld : nullptr;
-        float* of = p.out_f32 ? p.out_f32 + dst * ld : nullptr;
-        const bool relu = p.relu != 0;
+      // every MMA has completed (last acc_full) and with it every TMA write: the stage buffers are free -> staging tile
 #pragma unroll
-        for (int t = 0; t < NJT; t += 4) {
-          if (t < NJ) {
-            float4 v = make_float4(sum[t], sum[t + 1], sum[t + 2], sum[t + 3]);
-            if (bias) { const float4 b4 = *reinterpret_cast<const float4*>(bias + t); v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
-            if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            if (mask) {
-              const float4 m4 = *reinterpret_cast<const float4*>(mask + t);
-              v.x = m4.x > 0.f ? v.x : 0.f; v.y = m4.y > 0.f ? v.y : 0.f; v.z = m4.z > 0.f ? v.z : 0.f; v.w = m4.w > 0.f ? v.w : 0.f;
-            }
-            if (of) *reinterpret_cast<float4*>(of + t) = v;
-            if (oh) {
-              float4 h, l;
-              split4(v, h, l);
-              *reinterpret_cast<float4*>(oh + t) = h;
-              *reinterpret_cast<float4*>(ol + t) = l;
-            }
-          }
-        }
-      }
+      for (int c = 0; c < NJT / 4; ++c) *stage_chunk<NJT>(stage_base, r, c) = make_float4(sum[4 * c], sum[4 * c + 1], sum[4 * c + 2], sum[4 * c + 3]);
     }
   } else if (any_conv) {
     // ---------------------------------------------------------------- converter warps: raw fp32 -> hi / lo in place
     const int ct = threadIdx.x - 6 * 32;
     const UmOperand oa = p.A, ob = p.B;
     const int red = (int)p.red_per_stage;
+    int s = 0, r0 = cta.r0;
+    uint32_t ph = 0;
+    uint8_t* st = stage_base;
+    dz::pdl_enter();
     for (int it = 0; it < nst; ++it) {
-      const int s = it % ST;
-      const uint32_t ph = (uint32_t)(it / ST) & 1u;
       mbar_wait(&full[s], ph);
-      uint8_t* st = stage_base + (size_t)s * stage_bytes;
-      const int r0 = cta.r0 + it * red;
       if (conv_a) convert_part(oa, st, r0, ct);
       if (conv_b) convert_part(ob, st + a_bytes, r0, ct);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&ready[s]);
+      r0 += red;
+      ++s; st += stage_bytes;
+      if (s == ST) { s = 0; ph ^= 1u; st = stage_base; }
     }
   }
-  if (trace && blockIdx.x == 0 && warp == 2 && lane == 0) trace[321] = clock64();                         // epilogue stores issued
+  if (!direct && warp >= 2) {
+    // ---------------------------------------------------------------- cooperative store phase (warps 2-13, 384 threads)
+    if (warp >= 6 && !any_conv) dz::pdl_enter();
+    bar_sync_coop();
+    const int tid = threadIdx.x - 64;
+    const int NJ = p.NJ, cpr = NJ >> 2;
+    const int items = 128 * cpr;
+    // idx -> (row, chunk) and row -> (outer, inner) without integer divisions: rows < 128, so a 16-bit reciprocal is exact
+    const uint32_t inv_cpr = (65536u + (uint32_t)cpr - 1u) / (uint32_t)cpr;
+    constexpr int kIters = (128 * (NJT / 4) + 383) / 384;
+    if (p.epi == UM_EPI_ROWS) {
+      const int pw = p.pw;
+      const long long ld = p.out_ld;
+      const bool relu = p.relu != 0;
+      const float* __restrict__ maskp = p.mask;
+      float* __restrict__ of = p.out_f32; float* __restrict__ oh = p.out_hi; float* __restrict__ ol = p.out_lo;
+      const uint32_t inv_pw = pw >= 128 ? 0u : (65536u + (uint32_t)pw - 1u) / (uint32_t)pw;
+#pragma unroll
+      for (int j = 0; j < kIters; ++j) {
+        const int idx = tid + j * 384;
+        if (idx >= items) continue;
+        const int r = (int)(((uint32_t)idx * inv_cpr) >> 16), c = idx - r * cpr;
+        const int ro = (int)(((uint32_t)r * inv_pw) >> 16), ri = r - ro * pw;
+        if (ro >= cta.ph_valid || ri >= cta.pw_valid) continue;
+        const long long o = ((long long)cta.row_base + (long long)ro * p.rs_outer + (long long)ri * p.rs_inner) * ld + 4 * c;
+        float4 v = *stage_chunk<NJT>(stage_base, r, c);
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        if (maskp) {
+          const float4 m4 = *reinterpret_cast<const float4*>(maskp + o);
+          v.x = m4.x > 0.f ? v.x : 0.f; v.y = m4.y > 0.f ? v.y : 0.f; v.z = m4.z > 0.f ? v.z : 0.f; v.w = m4.w > 0.f ? v.w : 0.f;
+        }
+        if (of) *reinterpret_cast<float4*>(of + o) = v;
+        if (oh) {
+          float4 h, l;
+          split4(v, h, l);
+          *reinterpret_cast<float4*>(oh + o) = h;
+          *reinterpret_cast<float4*>(ol + o) = l;
+        }
+      }
+    } else {
+      float* __restrict__ C = p.C + (long long)cta.split * p.split_stride;
+      const float* __restrict__ scale_i = p.scale_i;
+      const long long sc_i = p.sc_i, sc_j = p.sc_j;
+      const bool vec = sc_j == 1 && (sc_i & 3) == 0 && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll
+      for (int j = 0; j < kIters; ++j) {
+        const int idx = tid + j * 384;
+        if (idx >= items) continue;
+        const int r = (int)(((uint32_t)idx * inv_cpr) >> 16), c = idx - r * cpr;
+        const int i = cta.i0 + r;
+        if (i >= p.MI) continue;
+        float4 v = *stage_chunk<NJT>(stage_base, r, c);
+        if (scale_i) { const float s = scale_i[i]; v.x *= s; v.y *= s; v.z *= s; v.w *= s; }
+        float* dst = C + (long long)i * sc_i + (long long)(4 * c) * sc_j;
+        if (vec) *reinterpret_cast<float4*>(dst) = v;
+        else { dst[0] = v.x; dst[sc_j] = v.y; dst[2 * sc_j] = v.z; dst[3 * sc_j] = v.w; }
+      }
+    }
+  }
+  if (tr && warp == 2 && lane == 0) trace[321] = clock64();                                         // stores issued
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
-  if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[322] = clock64();
+  if (tr && threadIdx.x == 0) trace[322] = clock64();
 }
 
 }  // namespace um

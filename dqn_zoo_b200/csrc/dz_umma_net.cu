@@ -115,13 +115,13 @@ struct Conv1Args {
   int blob[3];
   float *out_hi, *out_lo, *out_f32;
   int npass, B, W, oh, ow, m_pass, tiles_per_pass, ntiles, stag_bytes;
+  long long* trace;                // debug: clock stamps of CTA 0
 };
 
-constexpr int kC1W = 65536, kC1A = 131072;
+constexpr int kC1W = 65536, kC1A = 131072, kC1Epi = 4096;
 
 __global__ void __launch_bounds__(kThreadsU, 1) conv1_umma_kernel(const __grid_constant__ Conv1Args a) {
   if (threadIdx.x < 4) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.wmap[threadIdx.x >> 1][threadIdx.x & 1])) : "memory");
-  dz::pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_umma_kernel(const __grid_c
   uint8_t* w_smem = smem + 1024;
   uint8_t* a_smem = w_smem + kC1W;
   uint8_t* stag = a_smem + kC1A;
+  uint8_t* epi_smem = stag + 2 * (size_t)a.stag_bytes;       // 4 x 1 KB transposition patches of the epilogue warps
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 1) {
@@ -153,6 +154,9 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_umma_kernel(const __grid_c
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  dz::pdl_enter();                        // set-up above overlaps the previous kernel's tail; data accesses start here
+  const bool tr = a.trace != nullptr && blockIdx.x == 0;
+  if (tr && threadIdx.x == 0) { a.trace[323] = clock64(); a.trace[324] = clock64(); }
 
   const int px = a.oh * a.ow;             // output pixels per image
   const int row_bytes = a.W * 4;          // one input row of 4-channel pixels
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_umma_kernel(const __grid_c
       const int pass = tile / a.tiles_per_pass;
       const int m0 = (tile - pass * a.tiles_per_pass) * 128, m1 = min(m0 + 128, a.m_pass);
       mbar_wait(&raw_empty[buf], (((uint32_t)n >> 1) & 1u) ^ 1u);
-      if (lane == 0) {
+      if (elect_one()) {
         const int b0 = m0 / px, b1 = (m1 - 1) / px;
         uint32_t total = 0;
         for (int b = b0; b <= b1; ++b) {
@@ -185,14 +189,18 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_umma_kernel(const __grid_c
           bulk_g2s(dst0 + off, a.rows[pass][b] + (size_t)(4 * oy0) * row_bytes, bytes, &raw_full[buf]);
           off += bytes;
         }
+        if (tr && n < 64) a.trace[n] = clock64();                                                   // [0,64): row copies issued
       }
+      __syncwarp();
       if (pass != cur_pass) {
         if (n > 0) mbar_wait(&a_empty[3], ((uint32_t)(n - 1)) & 1u);   // previous tile's MMAs are done with the old image
-        if (lane == 0) mbar_expect_tx(w_full, (uint32_t)kC1W);
-        __syncwarp();
-        if (lane < 16) {
-          const int part = lane >> 3, s = lane & 7;
-          tma_load_5d(smem_u32(w_smem) + part * 32768 + s * 4096, &a.wmap[a.blob[pass]][part], w_full, 32 * s, 0, 0, 0, 0);
+        if (elect_one()) {
+          mbar_expect_tx(w_full, (uint32_t)kC1W);
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int part = q >> 3, s = q & 7;
+            tma_load_5d(smem_u32(w_smem) + part * 32768 + s * 4096, &a.wmap[a.blob[pass]][part], w_full, 32 * s, 0, 0, 0, 0);
+          }
         }
         cur_pass = pass;
       }
@@ -210,21 +218,28 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_umma_kernel(const __grid_c
         const int g = n * 8 + slab, buf = g & 1;
         mbar_wait(&acc_empty[buf], (((uint32_t)g >> 1) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (lane == 0) {
-          const uint32_t ab = smem_u32(a_smem) + slab * 16384, wh = smem_u32(w_smem) + slab * 4096, wl = wh + 32768;
+        if (elect_one()) {
+          // descriptor words: upper = SBO 1024 | version | SWIZZLE_128B, lower = LBO 16 | address >> 4 (advanced with adds)
+          constexpr uint32_t up = (1024u >> 4) | (1u << 14) | (2u << 29);
+          uint32_t al = (1u << 16) + ((smem_u32(a_smem) + slab * 16384) >> 4);
+          uint32_t wh = (1u << 16) + ((smem_u32(w_smem) + slab * 4096) >> 4), wl = wh + (32768u >> 4);
           const uint32_t d = tmem_base + (uint32_t)(buf * 32);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t da = make_desc_sw128(ab + k * 32, 16, 1024);
-            mma_tf32(d, da, make_desc_sw128(wl + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
-            mma_tf32(d, da, make_desc_sw128(wh + k * 32, 16, 1024), idesc, 1u);
+            const uint64_t da = ((uint64_t)up << 32) | al;
+            mma_tf32(d, da, ((uint64_t)up << 32) | wl, idesc, k > 0 ? 1u : 0u);
+            mma_tf32(d, da, ((uint64_t)up << 32) | wh, idesc, 1u);
+            al += 2; wh += 2; wl += 2;
           }
           mma_commit(&acc_full[buf]);
           if (slab & 1) mma_commit(&a_empty[slab >> 1]);
+          if (slab == 7 && tile == t_end - 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         }
         __syncwarp();
       }
+      if (tr && lane == 0 && n < 64) a.trace[128 + n] = clock64();                                  // [128,192): tile's MMAs issued
     }
+    if (t_begin >= t_end && elect_one()) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   } else if (warp < 6) {
     // ---------------------------------------------------------------- epilogue
     const int quarter = warp & 3;
@@ -232,8 +247,14 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_umma_kernel(const __grid_c
       const int pass = tile / a.tiles_per_pass;
       const int m0 = (tile - pass * a.tiles_per_pass) * 128, m1 = min(m0 + 128, a.m_pass);
       float sum[32];
+      {   // the bias is the initial value of the row sums (loaded while the tile's first MMAs are in flight)
+        const float* __restrict__ bias = a.bias[pass];
 #pragma unroll
-      for (int t = 0; t < 32; ++t) sum[t] = 0.f;
+        for (int t = 0; t < 32; t += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias + t);
+          sum[t] = b4.x; sum[t + 1] = b4.y; sum[t + 2] = b4.z; sum[t + 3] = b4.w;
+        }
+      }
       for (int slab = 0; slab < 8; ++slab) {
         const int g = n * 8 + slab, buf = g & 1;
         mbar_wait(&acc_full[buf], ((uint32_t)g >> 1) & 1u);
@@ -247,21 +268,35 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_umma_kernel(const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
       }
-      const int m = m0 + quarter * 32 + lane;
-      if (m < m1) {
-        const long long dst = ((long long)pass * a.m_pass + m) * 32;
-        const float* bias = a.bias[pass];
+      if (tr && warp == 2 && lane == 0 && n < 64) a.trace[192 + n] = clock64();                     // [192,256): tile drained
+      // The warp's 32 rows x 32 channels are ONE contiguous 4 KB block of act1: transpose it, 8 channels at a time, through
+      // a private XOR-swizzled 1 KB patch of shared memory (all that is left next to the 128 KB A tile), so that a store
+      // instruction writes 16 rows x 32 contiguous bytes (full sectors) instead of 32 rows x 16 bytes.
+      float4* patch = reinterpret_cast<float4*>(epi_smem + (warp - 2) * 1024);
+      const int mw0 = m0 + quarter * 32;                       // first row of this warp's block
+      const long long dst0 = ((long long)pass * a.m_pass + mw0) * 32;
 #pragma unroll
-        for (int t = 0; t < 32; t += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias + t);
-          float4 v = make_float4(fmaxf(sum[t] + b4.x, 0.f), fmaxf(sum[t + 1] + b4.y, 0.f), fmaxf(sum[t + 2] + b4.z, 0.f), fmaxf(sum[t + 3] + b4.w, 0.f));
-          float4 h, l;
-          split4(v, h, l);
-          *reinterpret_cast<float4*>(a.out_f32 + dst + t) = v;
-          *reinterpret_cast<float4*>(a.out_hi + dst + t) = h;
-          *reinterpret_cast<float4*>(a.out_lo + dst + t) = l;
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int t = q * 8 + cc * 4;
+          patch[lane * 2 + (cc ^ ((lane >> 2) & 1))] = make_float4(fmaxf(sum[t], 0.f), fmaxf(sum[t + 1], 0.f), fmaxf(sum[t + 2], 0.f), fmaxf(sum[t + 3], 0.f));
         }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int row = j * 16 + (lane >> 1), cc = lane & 1;
+          if (mw0 + row < m1) {
+            const float4 v = patch[row * 2 + (cc ^ ((row >> 2) & 1))];
+            float4 h, l;
+            split4(v, h, l);
+            *reinterpret_cast<float4*>(a.out_hi + dst0 + row * 32 + q * 8 + 4 * cc) = h;
+            *reinterpret_cast<float4*>(a.out_lo + dst0 + row * 32 + q * 8 + 4 * cc) = l;
+          }
+        }
+        __syncwarp();
       }
+      if (tr && warp == 2 && lane == 0 && n < 64) a.trace[256 + n] = clock64();                     // [256,320): tile stored
     }
   } else {
     // ---------------------------------------------------------------- converters: uint8 rows -> exact tf32 A tile
@@ -286,6 +321,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_umma_kernel(const __grid_c
         src_off = off + (4 * (oy - plo / a.ow)) * row_bytes + 16 * ox;
       }
       mbar_wait(&raw_full[buf], ((uint32_t)n >> 1) & 1u);
+      if (tr && ct == 0 && n < 64) a.trace[64 + n] = clock64();                                     // [64,128): input rows landed
       const uint8_t* src = stag + (size_t)buf * a.stag_bytes + src_off;
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
@@ -323,6 +359,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_umma_kernel(const __grid_c
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64) : "memory");
   }
+  if (tr && threadIdx.x == 0) a.trace[322] = clock64();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -342,7 +379,6 @@ constexpr int kC1G = 32768;      // dact1 tile: hi | lo, [128 rows][32 n] each
 
 __global__ void __launch_bounds__(kThreadsU, 1) conv1_wgrad_umma_kernel(const __grid_constant__ Conv1WgArgs a) {
   if (threadIdx.x < 2) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&a.gmap[threadIdx.x])) : "memory");
-  dz::pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -374,6 +410,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_wgrad_umma_kernel(const __
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  dz::pdl_enter();                        // set-up above overlaps the previous kernel's tail; data accesses start here
 
   const int px = a.oh * a.ow;
   const int row_bytes = a.W * 4;
@@ -386,7 +423,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_wgrad_umma_kernel(const __
       const int buf = n & 1;
       const int m0 = tile * 128, m1 = min(m0 + 128, a.m_pass);
       mbar_wait(&raw_empty[buf], (((uint32_t)n >> 1) & 1u) ^ 1u);
-      if (lane == 0) {
+      if (elect_one()) {
         const int b0 = m0 / px, b1 = (m1 - 1) / px;
         uint32_t total = 0;
         for (int b = b0; b <= b1; ++b) {
@@ -404,10 +441,13 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_wgrad_umma_kernel(const __
           off += bytes;
         }
       }
-      if (n > 0) mbar_wait(t_done, ((uint32_t)(n - 1)) & 1u);
-      if (lane == 0) mbar_expect_tx(g_full, (uint32_t)kC1G);
       __syncwarp();
-      if (lane < 2) tma_load_5d(smem_u32(g_smem) + lane * 16384, &a.gmap[lane], g_full, 0, m0, 0, 0, 0);
+      if (n > 0) mbar_wait(t_done, ((uint32_t)(n - 1)) & 1u);
+      if (elect_one()) {
+        mbar_expect_tx(g_full, (uint32_t)kC1G);
+        tma_load_5d(smem_u32(g_smem), &a.gmap[0], g_full, 0, m0, 0, 0, 0);
+        tma_load_5d(smem_u32(g_smem) + 16384, &a.gmap[1], g_full, 0, m0, 0, 0, 0);
+      }
       __syncwarp();
     }
   } else if (warp == 1) {
@@ -421,17 +461,23 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_wgrad_umma_kernel(const __
         const int g = n * 2 + mt, buf = g & 1;
         mbar_wait(&acc_empty[buf], (((uint32_t)g >> 1) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (lane == 0) {
-          const uint32_t ab = smem_u32(a_smem) + mt * 4 * 16384, gh = smem_u32(g_smem), gl = gh + 16384;
+        if (elect_one()) {
+          // descriptor words: upper = SBO 512 | version | 32-byte-atom swizzle, lower = LBO 16384 | address >> 4
+          constexpr uint32_t up = (512u >> 4) | (1u << 14) | (1u << 29);
+          constexpr uint32_t lbo = (16384u >> 4) << 16;
+          uint32_t al = lbo + ((smem_u32(a_smem) + mt * 4 * 16384) >> 4);
+          uint32_t gh = lbo + (smem_u32(g_smem) >> 4), gl = gh + (16384u >> 4);
           const uint32_t d = tmem_base + (uint32_t)(buf * 64 + mt * 32);
 #pragma unroll 4
           for (int k = 0; k < 16; ++k) {
-            const uint64_t da = make_desc_sw128(ab + k * 1024, 16384, 512, 1);
-            mma_tf32(d, da, make_desc_sw128(gl + k * 1024, 16384, 512, 1), idesc, k > 0 ? 1u : 0u);
-            mma_tf32(d, da, make_desc_sw128(gh + k * 1024, 16384, 512, 1), idesc, 1u);
+            const uint64_t da = ((uint64_t)up << 32) | al;
+            mma_tf32(d, da, ((uint64_t)up << 32) | gl, idesc, k > 0 ? 1u : 0u);
+            mma_tf32(d, da, ((uint64_t)up << 32) | gh, idesc, 1u);
+            al += 64; gh += 64; gl += 64;
           }
           mma_commit(&acc_full[buf]);
           if (mt == 1) mma_commit(t_done);
+          if (mt == 1 && tile == t_end - 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         }
         __syncwarp();
       }
@@ -597,16 +643,20 @@ __global__ void __launch_bounds__(256) um_fcd_finish_kernel(const float* __restr
 // as a deterministic two-level column sum of the (fp32) output gradient: 128-row chunks in parallel, the last block to
 // finish adds the chunk sums in chunk order.  One launch covers several layers: blockIdx.y = layer; blocks
 // [0, kWgSumBlocks) add the partials, blocks beyond do the bias chunks.
-constexpr int kWgSumBlocks = 36, kWgChunkRows = 128, kWgMaxChunks = 256;
+// Partial sums: a block owns 32 consecutive float4 columns; its 8 thread groups stride over the S partials (so the
+// up-to-148 loads of one column are 8 independent chains instead of one dependent chain), then group sums are added in
+// group order through shared memory — a fixed association, hence bit-deterministic.
+constexpr int kWgSumBlocks = 288, kWgChunkRows = 128, kWgMaxChunks = 256, kWgGroups = 8;
 struct WgFinish { const float* partial; int S; long long stride; int KN; float* dW; const float* G; int M, N; float* db; float* scratch; unsigned int* ticket; };
 struct WgFinishBatch { WgFinish f[4]; int n; };
 
 __global__ void __launch_bounds__(256) um_wgrad_finish_kernel(const __grid_constant__ WgFinishBatch b) {
   dz::pdl_enter();
   const WgFinish& f = b.f[blockIdx.y];
-  __shared__ float red[256];
+  __shared__ float4 red4[256];
   __shared__ bool last;
   if (blockIdx.x >= kWgSumBlocks) {
+    float* red = reinterpret_cast<float*>(red4);
     const int chunk = blockIdx.x - kWgSumBlocks, nchunks = (f.M + kWgChunkRows - 1) / kWgChunkRows;
     if (!f.db || chunk >= nchunks) return;
     const int n = threadIdx.x % f.N, g = threadIdx.x / f.N, G = 256 / f.N;
@@ -626,23 +676,42 @@ __global__ void __launch_bounds__(256) um_wgrad_finish_kernel(const __grid_const
     __syncthreads();
     if (last) {
       __threadfence();
+      // chunk sums: G thread groups stride over the chunks (independent L2 loads), group sums added in group order
+      float t = 0.f;
+#pragma unroll 4
+      for (int c = g; c < nchunks; c += G) t += __ldcg(f.scratch + c * 64 + n);
+      red[threadIdx.x] = t;
+      __syncthreads();
       if (threadIdx.x < f.N) {
-        float t = 0.f;
-        for (int c = 0; c < nchunks; ++c) t += ((volatile float*)f.scratch)[c * 64 + threadIdx.x];
-        f.db[threadIdx.x] = t;
+        float tt = 0.f;
+        for (int q = 0; q < G; ++q) tt += red[q * f.N + threadIdx.x];
+        f.db[threadIdx.x] = tt;
       }
       if (threadIdx.x == 0) *f.ticket = 0;
     }
     return;
   }
   const int total4 = f.KN >> 2;
-  for (int i4 = blockIdx.x * 256 + threadIdx.x; i4 < total4; i4 += kWgSumBlocks * 256) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = 0; s < f.S; ++s) {
-      const float4 x = *reinterpret_cast<const float4*>(f.partial + s * f.stride + ((long long)i4 << 2));
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;
+  if (blockIdx.x * 32 >= total4) return;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < total4) {
+    const float* src = f.partial + ((long long)col << 2);
+#pragma unroll 4
+    for (int s = g; s < f.S; s += kWgGroups) {
+      const float4 x = *reinterpret_cast<const float4*>(src + s * f.stride);
       v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
     }
-    *reinterpret_cast<float4*>(f.dW + ((long long)i4 << 2)) = v;
+  }
+  red4[threadIdx.x] = v;
+  __syncthreads();
+  if (g == 0 && col < total4) {
+#pragma unroll
+    for (int q = 1; q < kWgGroups; ++q) {
+      const float4 x = red4[q * 32 + threadIdx.x];
+      v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+    }
+    *reinterpret_cast<float4*>(f.dW + ((long long)col << 2)) = v;
   }
 }
 
@@ -676,7 +745,7 @@ bool um_net_supported(const UmNetDesc& d) {
     }
     worst = std::max(worst, tot);
   }
-  if (worst > 14 * 1024) return false;
+  if (2 * ((worst + 127) / 128 * 128) + 2048 + 65536 + 131072 + 4096 > 227 * 1024) return false;
   return true;
 }
 
@@ -800,7 +869,7 @@ int build_plan(UmNet* n) {
       memset(&pr, 0, sizeof(pr));
       pr.A = A; pr.B = Bo; pr.ksteps = 4; pr.run_stages = 1; pr.red_per_stage = 32; pr.epi = UM_EPI_ROWS;
       pr.MI = rows; pr.NJ = 64;
-      pr.out_hi = n->act_hi[1]; pr.out_lo = n->act_lo[1]; pr.out_f32 = n->act_f32[1]; pr.out_ld = 64;
+      pr.out_hi = n->act_hi[1]; pr.out_lo = n->act_lo[1]; pr.out_f32 = nullptr; pr.out_ld = 64;
       pr.bias = (blob ? d.target : d.online) + d.off_conv_b[1]; pr.relu = 1;
       pr.pw = 1 << 20; pr.rs_outer = 0; pr.rs_inner = 1;
       const int prob = (int)pl.probs.size();
@@ -1251,7 +1320,7 @@ int um_net_create(const UmNetDesc& d, char* base, UmNet** out) {
     }
     worst = std::max(worst, tot);
   }
-  n->conv1_stag_bytes = (worst + 1023) / 1024 * 1024;
+  n->conv1_stag_bytes = (worst + 127) / 128 * 128;
   cudaMemset(n->wg_ticket, 0, 64 * 4);
   // gradient buffers start as zeros (hi/lo pairs of layers whose producer has not run yet are never NaN)
   for (int L = 0; L < 3; ++L) {
@@ -1286,9 +1355,11 @@ void um_net_destroy(UmNet* n) {
   delete n;
 }
 
+// Layers 1 and 2 have no consumer of the exact fp32 activation on this path (the next layer reads the hi/lo pair, the
+// ReLU masks read the sign of hi): their "fp32 view" is the tf32 hi image — same activation pattern, values rounded to tf32.
 float* um_act_f32(UmNet* n, int layer, int pass) {
   const int64_t per[3] = {(int64_t)n->d.B * n->h1 * n->w1 * 32, (int64_t)n->d.B * n->h2 * n->w2 * 64, (int64_t)n->d.B * n->feat};
-  return n->act_f32[layer - 1] + per[layer - 1] * pass;
+  return (layer < 3 ? n->act_hi[layer - 1] : n->act_f32[layer - 1]) + per[layer - 1] * pass;
 }
 float* um_dact_f32(UmNet* n, int layer) { return n->dact_f32[layer - 1]; }
 float* um_h1_f32(UmNet* n, int pass, int stream) { return n->h1_buf + ((int64_t)pass * n->d.nstream + stream) * n->d.B * 512; }
@@ -1322,7 +1393,8 @@ int um_forward_torso(UmNet* n, const uint8_t* const* const* rows, void* stream) 
   a.out_hi = n->act_hi[0]; a.out_lo = n->act_lo[0]; a.out_f32 = n->act_f32[0];
   a.npass = d.npass; a.B = d.B; a.W = d.W; a.oh = n->h1; a.ow = n->w1; a.m_pass = d.B * n->h1 * n->w1;
   a.tiles_per_pass = n->conv1_tiles_per_pass; a.ntiles = a.tiles_per_pass * d.npass; a.stag_bytes = n->conv1_stag_bytes;
-  const size_t smem = 2048 + kC1W + kC1A + 2 * (size_t)a.stag_bytes;
+  a.trace = n->tr("conv1_fwd");
+  const size_t smem = 2048 + kC1W + kC1A + 2 * (size_t)a.stag_bytes + kC1Epi;
   if (smem > 227 * 1024) return fail(DZ_EINVAL, "conv1 staging does not fit");
   const unsigned grid = (unsigned)std::min(148, a.ntiles);
   DZ_LAUNCH_NAMED("conv1_fwd", conv1_umma_kernel, grid, kThreadsU, smem, stream, a);

@@ -33,7 +33,7 @@ void um_net_destroy(UmNet* n);
 void um_net_trace(UmNet* n, const char* tag, long long* d_trace);   // debug: clock stamps of CTA 0 of the launch `tag`
 
 // Buffers the rest of the learner reads / writes (fp32 views of the activations and gradients).
-float* um_act_f32(UmNet* n, int layer, int pass);      // layer 1..3 -> [B][h][w][C]
+float* um_act_f32(UmNet* n, int layer, int pass);      // layer 1..3 -> [B][h][w][C] (layers 1, 2: the tf32 hi image)
 float* um_dact_f32(UmNet* n, int layer);               // layer 1..3: d loss / d (pre-ReLU masked) activation of pass 0
 float* um_h1_f32(UmNet* n, int pass, int stream);      // [B][512] (post-ReLU)
 float* um_dh1_f32(UmNet* n, int stream);               // [B][512] gradient wrt h1 (already masked), INPUT of um_backward_fc

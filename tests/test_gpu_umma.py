@@ -72,3 +72,13 @@ def test_row_epilogue_bias_relu_and_split_outputs(run_stages):
   assert np.all((hi.astype(np.float32).view(np.uint32) & 0x1FFF) == 0)
   assert np.all((lo.astype(np.float32).view(np.uint32) & 0x1FFF) == 0)
   np.testing.assert_allclose(hi + lo, got, rtol=3e-7, atol=1e-30)
+
+
+@pytest.mark.parametrize('kind', ['dqn', 'double_q', 'c51', 'qrdqn', 'rainbow', 'iqn'])
+def test_tcgen05_path_is_active_at_the_baseline_geometry(kind):
+  """The 84x84x4, batch-32 learner of BASELINE.json must run its torso (and 3136->512 layer) on the tcgen05 kernels:
+  a silent fall-back to the fp32-FMA kernels (geometry check, shared-memory budget) would keep every parity test green."""
+  from dqn_zoo_b200 import _lib
+  from dqn_zoo_b200 import learner as dl
+  L = dl.Learner(dl.NetworkSpec(kind, 6), batch_size=32)
+  _lib.call('dz_test_learner_trace', L._h, b'', 0)   # raises ValueError when the path is not active

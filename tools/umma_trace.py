@@ -34,6 +34,12 @@ def main():
     t = tr.cpu().numpy()
     t0 = t[323]
     rel = lambda x: int(x - t0) if x else -1
+    if tag.startswith('conv1'):
+      nt = int((t[192:256] != 0).sum())
+      print('== %s: tiles %d | exit %d' % (tag, nt, rel(t[322])))
+      for name, o in (('rows issued', 0), ('rows landed', 64), ('mma issued', 128), ('tile drained', 192), ('tile stored', 256)):
+        print('  %-12s:' % name, [rel(x) for x in t[o:o + nt]])
+      continue
     n = int((t[:64] != 0).sum())
     runs = int((t[192:256] != 0).sum())
     print('== %s: stages %d runs %d | setup done %d | epilogue math %d stores %d exit %d' % (tag, n, runs, rel(t[324]), rel(t[320]), rel(t[321]), rel(t[322])))
