@@ -263,16 +263,25 @@ def main():
   clocks = ClockSampler(local_rank)
   clocks.start()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  # The target refresh (an NCCL broadcast at N > 1) must be inside every timed region, however short: it runs every
+  # `sync_every` = min(target period, K) steps, i.e. at least once (the reference's cadence is `target_period`).
+  sync_every = max(1, min(target_period, K))
+  coll_events = []
   barrier()
   e0.record()
   for i in range(K):
     ag.learn_from_device_draws(d_draws[W + i])
-    if (i + 1) % target_period == 0:
+    if (i + 1) % sync_every == 0:
+      c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      c0.record()
       sync_target()
+      c1.record()
+      coll_events.append((c0, c1))
   e1.record()
   barrier()
   clk = clocks.stop()
   ms = e0.elapsed_time(e1)
+  collective_us = 1e3 * float(np.mean([a.elapsed_time(b) for a, b in coll_events])) if coll_events else None
   t = torch.tensor([ms], dtype=torch.float64, device=device)
   if dist is not None:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -291,7 +300,7 @@ def main():
   for i in range(K):
     ag.learn()
     loss_host[i:i + 1].copy_(L.loss, non_blocking=True)
-    if (i + 1) % target_period == 0:
+    if (i + 1) % sync_every == 0:
       sync_target()
   e3.record()
   barrier()
@@ -322,6 +331,45 @@ def main():
   per_launch_us = {k: 1e3 * v[1] / v[0] for k, v in prof.items()}
   share = {k: round(v[1] / total_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}
 
+  # ---- (3b) device timeline of the CUDA-graph step: every kernel stamps %globaltimer when its dependencies have completed
+  # (dz_debug_timeline); a kernel's time = its start to the next start in the step (the last one: to the step's end).
+  # Eager per-launch events above include the host's launch latency whenever the host is the bottleneck (they read 52 us
+  # for a 37 us optimizer launch), so the roofline below uses the graph timeline and reports the event figure beside it.
+  graph_us, graph_share, graph_step_us = {}, {}, None
+  if not args.no_graph:
+    ag._use_graph = True
+    for i in range(5):
+      ag.learn()
+    torch.cuda.synchronize()
+    tl_steps = 40
+    tl = torch.zeros(2 + 2 * 4000, dtype=torch.int64, device=device)
+    _lib.call('dz_debug_timeline', tl.data_ptr())
+    for i in range(tl_steps):
+      ag.learn_from_device_draws(d_draws[i % (W + K)])
+    torch.cuda.synchronize()
+    _lib.call('dz_debug_timeline', 0)
+    t = tl.cpu().numpy()
+    n = int(t[0] & 0xffffffff)
+    per = n // tl_steps
+    if per * tl_steps == n and per > 0 and n <= 4000:
+      ts = t[2:2 + 2 * n:2].astype(np.int64)
+      sg = t[3:3 + 2 * n:2].astype(np.int64)
+      order = np.argsort(ts, kind='stable')
+      ts, sg = ts[order].reshape(tl_steps, per)[2:], sg[order].reshape(tl_steps, per)[2:]
+      graph_step_us = float(np.median(np.diff(ts[:, 0])) / 1e3)   # median: steps whose replay the host submitted late drop out
+      nxt = np.concatenate([ts[:, 1:], ts[:, :1] + int(round(graph_step_us * 1e3))], axis=1)
+      dur = np.median(nxt - ts, axis=0) / 1e3
+      by_geo = {}
+      for k, v in prof.items():
+        by_geo.setdefault((int(v[2]), int(v[3]), int(v[4])), []).append(k)
+      for j in range(per):
+        g = int(sg[-1, j])
+        names = by_geo.get((g >> 32, (g >> 16) & 0xffff, g & 0xffff), ['?'])
+        key = '/'.join(names)
+        graph_us[key] = graph_us.get(key, 0.0) + float(dur[j])
+      graph_share = {k: round(v / graph_step_us, 4) for k, v in sorted(graph_us.items(), key=lambda kv: -kv[1])[:8]}
+    ag._use_graph = False
+
   hbm_peak, tf_peak, peak_src = measured_peaks()
   # Dominant-kernel roofline.  Algorithmic bytes per launch of each candidate:
   P = L.plan.param_count
@@ -339,10 +387,21 @@ def main():
   }
   name = top[0]
   dur_s = 1e-3 * top[1][1] / top[1][0]
-  traffic = None
+  event_us = 1e6 * dur_s
+  timing_source = 'cuda events around each eager launch (dz_profile)'
+  single = {k: v for k, v in graph_us.items() if '/' not in k and k in prof}
+  if single:
+    # stable choice: the kernel with the largest share of the graph-replayed step; per-launch time = its share / launches
+    name = max(single.items(), key=lambda kv: kv[1])[0]
+    launches_in_step = max(1, int(round(prof[name][0] / prof_steps)))
+    dur_s = 1e-6 * single[name] / launches_in_step
+    event_us = 1e3 * prof[name][1] / prof[name][0]
+    timing_source = 'device %globaltimer stamps inside the CUDA-graph step (dz_debug_timeline)'
+  traffic, ncu_facts = None, {}
   try:
-    with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
-      traffic = json.load(f).get(args.agent, {}).get(name)
+    with open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')) as f:
+      ncu_facts = json.load(f).get(args.agent, {})
+    traffic = ncu_facts.get('dram_bytes', {}).get(name)
   except Exception:
     traffic = None
   # dense-contraction kernels: algorithmic FLOPs per launch (2*M*N*K per problem, SURVEY §2.1 shapes)
@@ -377,11 +436,24 @@ def main():
     roofline = {'kernel': name, 'bound': 'tensor', 'achieved': achieved, 'peak': tf_peak, 'unit': 'TFLOP/s',
                 'frac': achieved / tf_peak, 'traffic': traffic, 'avg_launch_us': 1e6 * dur_s, 'peak_source': peak_src,
                 'note': 'whole-step algorithmic FLOPs over summed kernel time'}
-  roofline['kernel_time_share'] = share
+  roofline['kernel_time_share'] = graph_share or share
+  roofline['timing_source'] = timing_source
+  roofline['event_us_eager'] = event_us
+  # north-star fields: HBM GB/s on sample + gather, tensor-pipe % on the conv stack, whole-step HBM fraction
+  gather_bytes = 2 * B * 28224 + 12 * B + (20480 if AGENT_SETUP[args.agent][0] else 0)
+  sampler = 'per_sample_kernel' if AGENT_SETUP[args.agent][0] else 'uniform_sample_kernel'
+  sg_us = (graph_us.get(sampler, per_launch_us.get(sampler, float('nan'))) +
+           graph_us.get('conv1_fwd', per_launch_us.get('conv1_fwd', float('nan'))))
+  roofline['sample_gather_gbs'] = gather_bytes / (sg_us * 1e-6) / 1e9
   roofline['sample_gather'] = {
-      'alg_bytes_per_step': 2 * B * 28224 + 12 * B + (20480 if AGENT_SETUP[args.agent][0] else 0),
-      'note': 'gather is fused into conv1_fwd/conv1_wgrad operand loads; sampler kernel avg us = %.2f'
-              % per_launch_us.get('per_sample_kernel', per_launch_us.get('uniform_sample_kernel', float('nan')))}
+      'alg_bytes_per_step': gather_bytes, 'us': sg_us, 'frac_of_hbm_peak': gather_bytes / (sg_us * 1e-6) / 1e9 / hbm_peak,
+      'note': 'sampler kernel + conv1_fwd (the gather of the sampled rows IS conv1_fwd\'s bulk-copy operand load): '
+              'latency-bound at batch 32 (1.8 MB per step)'}
+  step_bytes = sum(alg_bytes[k] * max(1, int(round(prof[k][0] / prof_steps))) for k in alg_bytes if k in prof)
+  step_s = (graph_step_us * 1e-6) if graph_step_us else (ms_max / K / 1e3)
+  roofline['step_hbm_frac'] = step_bytes / step_s / 1e9 / hbm_peak
+  roofline['step_alg_bytes'] = step_bytes
+  roofline['conv_tensor_pipe_pct'] = ncu_facts.get('tensor_pipe_pct')   # ncu sm__pipe_tensor_cycles_active of this build (profiles/)
 
   # ---- (4) CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------
   cpu = None
@@ -400,13 +472,13 @@ def main():
         'sampled_transitions_per_sec': value * B, 'n_gpus': world, 'steps': K, 'warmup': W,
         'ms_per_step': ms_max / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32 (f64 sum tree)', 'data': 'synthetic',
-        'config': {'workload': workload_name(args), 'agent': args.agent, 'replay_capacity': args.capacity, 'batch': B,
-                   'replay_bytes_per_gpu': int(rep._store.obs.numel()), 'cuda_graph': not args.no_graph,
-                   'l2': 'inputs larger than L2: 56.4 GB replay store sampled at random rows; the %.1f MB of '
-                         'parameters+optimizer state stay L2-resident as in steady-state training' % (7 * 4 * P / 1e6),
-                   'multi_gpu': 'independent replay+learner shard per rank; NCCL broadcast of the target blob every %d '
-                                'learner steps' % target_period,
-                   'seed': args.seed},
+        'config': config_of(args, target_period),
+        'run': {'cuda_graph': not args.no_graph, 'replay_bytes_allocated': int(rep._store.obs.numel()),
+                'optimizer_state_mb': 7 * 4 * P / 1e6, 'target_sync_every_steps_in_timed_region': sync_every,
+                'target_syncs_in_timed_region': len(coll_events), 'collective_us': collective_us,
+                'collective': ('ncclBroadcast of the %.1f MB online blob into every rank\'s target' % (4 * P / 1e6)) if world > 1
+                              else 'device-to-device copy online -> target (one rank)'},
+        'collective_us': collective_us,
         'clocks': clk,
         'e2e': {'value': e2e_value, 'unit': 'grad-steps/s', 'h2d_bytes_per_step': stage_bytes, 'd2h_bytes_per_step': 4,
                 'note': 'agent.learn(): host RandomState draws -> pinned -> H2D; async D2H of the loss each step'},
@@ -414,6 +486,8 @@ def main():
         'gpu_launches_per_step': launches_per_step,
         'roofline': roofline,
         'kernel_avg_us': {k: round(v, 2) for k, v in per_launch_us.items()},
+        'kernel_graph_us': {k: round(v, 2) for k, v in graph_us.items()},
+        'graph_step_us': graph_step_us,
         'learner_gflop_per_step': GFLOP_PER_STEP[args.agent],
         'learner_tflops_achieved': GFLOP_PER_STEP[args.agent] * value / world / 1e3,
         'cpu_baseline': cpu,

@@ -103,6 +103,7 @@ _SIGNATURES = {
     'dz_learner_update': (i32, [vp, C.POINTER(Batch), C.POINTER(UpdateOutputs), i32, vp]),
     'dz_learner_learn': (i32, [vp, C.POINTER(ReplayView), i32, C.POINTER(LearnIO), vp]),
     'dz_learner_generate_randomness': (i32, [vp, u64, vp, vp, vp]),
+    'dz_learner_generate_randomness_async': (i32, [vp, u64, vp, vp, vp]),
     'dz_learner_q_values': (i32, [vp, vp, vp, vp, vp, vp]),
     'dz_learner_sync_target': (i32, [vp, vp]),
     'dz_test_u8_to_unit': (i32, [vp, vp]),

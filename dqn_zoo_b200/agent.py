@@ -291,7 +291,7 @@ class _DeviceAgent(parts.Agent):
     if getattr(self, '_jax_key', None) is not None:
       self._jax_learn.launch(L.taus)            # jax.random.uniform draws from the keys staged by _learn()
     elif self.KIND in ('iqn', 'rainbow'):
-      L.generate_randomness(self._seed)
+      L.generate_randomness(self._seed, beside_sampler=True)
     L.learn(self._view, self.PRIORITIZED, self._io)
 
   def check_device_flags(self):

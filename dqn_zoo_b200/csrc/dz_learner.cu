@@ -2165,6 +2165,7 @@ int update_impl(dz_learner* l, const dz_batch* batch, const dz_update_outputs* o
   if (c.kind == DZ_RAINBOW && !batch->d_noise) return fail(DZ_EINVAL, "rainbow update needs d_noise");
   if (c.kind == DZ_IQN && !batch->d_taus) return fail(DZ_EINVAL, "iqn update needs d_taus");
   if (!out || !out->d_loss || !out->d_per_example) return fail(DZ_EINVAL, "update outputs d_loss and d_per_example are required");
+  if (!(weights_packed && l->um != nullptr)) DZ_TRY(join_side(l, stream));   // pending side-stream work (asynchronous randomness)
 
   // ---- forward: every network.apply of loss_fn in grouped launches
   TorsoJob jobs[3];
@@ -2179,7 +2180,13 @@ int update_impl(dz_learner* l, const dz_batch* batch, const dz_update_outputs* o
     for (int i = 0; i < nj; ++i) rows[i] = jobs[i].rows;
     if (weights_packed) DZ_TRY(join_side(l, stream));   // packed on the side stream, concurrently with the sampler
     else DZ_TRY(um_pack_weights(l->um, stream));
+    // Optional (DZ_PREFETCH=1): pull the 3136 -> 512 weight matrices into L2 beside the conv stack.  Measured on the
+    // rainbow step: no gain (noisy1_fwd 23.0 vs 22.2 us, step 253 vs 244 us) — the layer is bound by its per-CTA pipeline,
+    // not by DRAM — so it is off by default.
+    static const bool prefetch = getenv("DZ_PREFETCH") != nullptr && getenv("DZ_PREFETCH")[0] == '1';
+    if (prefetch && c.kind != DZ_IQN && l->side) DZ_TRY(um_prefetch_fc(l->um, fork_side(l, stream)));
     DZ_TRY(um_forward_torso(l->um, rows, stream));
+    DZ_TRY(join_side(l, stream));
     if (c.kind != DZ_IQN) DZ_TRY(um_forward_fc(l->um, batch->d_noise, stream));
   } else {
     DZ_TRY(forward_torso(l, jobs, nj, B, stream));
@@ -2365,7 +2372,10 @@ int dz_learner_learn(dz_learner* l, const dz_replay_view* replay, int32_t priori
   if (replay->obs_bytes != (int64_t)l->d.H * l->d.W * l->d.C) return fail(DZ_EINVAL, "replay observation size does not match the network");
   // conv weight images do not depend on the sampled batch: pack them on the side stream while the sampler runs
   const bool pack_aside = l->um != nullptr && l->side != nullptr;
-  if (pack_aside) DZ_TRY(um_pack_weights(l->um, fork_side(l, stream)));
+  if (pack_aside) {
+    void* ws = fork_side(l, stream);
+    DZ_TRY(um_pack_weights(l->um, ws));
+  }
   DZ_TRY(launch_sample(replay, prioritized, &io->sample_in, &io->sample_out, B, ex, stream));
   dz_batch batch;
   batch.d_s_tm1_rows = l->rows_sample[0];
@@ -2377,6 +2387,14 @@ int dz_learner_learn(dz_learner* l, const dz_replay_view* replay, int32_t priori
   if (prioritized && !io->update_out.d_priorities) return fail(DZ_EINVAL, "prioritized learn needs update_out.d_priorities");
   DZ_TRY(update_impl(l, &batch, &io->update_out, 1, io->d_max_seen_priority, prioritized ? &wb : nullptr, stream, pack_aside));
   return DZ_OK;
+}
+
+// Same as dz_learner_generate_randomness, but enqueued on the learner's side stream (when it has one): the draws do not
+// depend on the sampled batch, so they run beside the sampler instead of in front of it.  Ordered after everything already
+// enqueued on `stream` and before the next dz_learner_learn / dz_learner_update / dz_learner_q_values on `stream`; any
+// other consumer of the buffers must synchronise the device first.
+int dz_learner_generate_randomness_async(dz_learner* l, uint64_t seed, float* d_taus, float* d_noise, void* stream) {
+  return dz_learner_generate_randomness(l, seed, d_taus, d_noise, fork_side(l, stream));
 }
 
 int dz_learner_generate_randomness(dz_learner* l, uint64_t seed, float* d_taus, float* d_noise, void* stream) {
@@ -2396,6 +2414,7 @@ int dz_learner_generate_randomness(dz_learner* l, uint64_t seed, float* d_taus, 
 int dz_learner_q_values(dz_learner* l, const uint8_t* d_obs, const float* d_taus, const float* d_noise, float* d_q_out, void* stream) {
   const dz_learner_config& c = l->cfg;
   const float* on = l->buf.d_online;
+  DZ_TRY(join_side(l, stream));   // pending side-stream work (asynchronous randomness)
   DZ_LAUNCH(make_row_table_kernel, 1, 32, 0, stream, d_obs, (long long)0, 1, l->rows_act);
   TorsoJob job{on, l->rows_act, 1};   // use activation set 1 so a pending backward's set-0 buffers stay intact
   DZ_TRY(forward_torso(l, &job, 1, 1, stream));

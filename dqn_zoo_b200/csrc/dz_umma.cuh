@@ -40,10 +40,13 @@ struct UmOperand {
   uint32_t part_bytes;    // bytes of one part (hi or lo) of a stage; multiple of 1024
   uint32_t nparts;        // 2: hi + lo;  1: exact operand (values are tf32 numbers, no lo part)
   uint32_t convert;       // 1: TMA delivers raw fp32 into part 0; converter warps split it into hi (in place) / lo (part 1)
+                          // 2: TMA delivers TWO raw tiles, mu into part 0 and sigma into part 1 (noisy layers, networks.py:
+                          //    137-178); the converters form w = mu + sigma * scale_r[r] * scale_i[i] and split THAT in place
   uint32_t mn_major;      // 0: K-major [rows][32 r];  1: MN-major slabs of [r rows][32 mn]
   uint32_t lbo;           // MN-major: bytes between 32-wide slabs (= r rows per stage * 128)
   uint32_t kstep;         // bytes added to the descriptor start per MMA k-step of 8 (K-major 32, MN-major 1024)
   const float* scale_r;   // convert only: element *= scale_r[reduction index] before the split (noisy sigma weights)
+  const float* scale_i;   // convert == 2 only: ... *= scale_i[row index of D / of the operand] (factorised noise, other factor)
 };
 
 enum : uint32_t { UM_EPI_PARTIAL = 0, UM_EPI_ROWS = 1 };
@@ -152,29 +155,95 @@ __device__ __forceinline__ void split4(const float4 x, float4& h, float4& l) {
   h.w = rn_tf32(x.w); l.w = rn_tf32(x.w - h.w);
 }
 
-// In-place hi/lo split of one raw operand part (a sequence of 128-byte swizzled rows).
-__device__ __forceinline__ void convert_part(const UmOperand& o, uint8_t* part0, int r0, int ct) {
+// In-place hi/lo split of one raw operand part (a sequence of 128-byte swizzled rows).  i0: MN index of the part's row 0.
+__device__ __forceinline__ void convert_part(const UmOperand& o, uint8_t* part0, int r0, int i0, int ct) {
   const int nchunks = (int)(o.part_bytes >> 4);
   const float* __restrict__ sc = o.scale_r;
+  const float* __restrict__ si = o.scale_i;
   const int rows_per_slab = (int)(o.lbo >> 7);
+  const bool dual = o.convert == 2;
   for (int idx = ct; idx < nchunks; idx += kConvWarps * 32) {
     float4* p = reinterpret_cast<float4*>(part0 + ((size_t)idx << 4));
+    float4* p1 = reinterpret_cast<float4*>(part0 + o.part_bytes + ((size_t)idx << 4));
     float4 x = *p;
-    if (sc) {
+    if (sc || dual) {
       const int row = idx >> 3;
-      if (o.mn_major) {          // rows are reduction indices
-        const float s = sc[r0 + (row % rows_per_slab)];
-        x.x *= s; x.y *= s; x.z *= s; x.w *= s;
+      float4 f = make_float4(1.f, 1.f, 1.f, 1.f);
+      if (o.mn_major) {          // rows are reduction indices, the 128 bytes of a row are 32 consecutive MN indices
+        const int slab = row / rows_per_slab, rr = row - slab * rows_per_slab;
+        if (sc) { const float s = sc[r0 + rr]; f.x = s; f.y = s; f.z = s; f.w = s; }
+        if (dual && si) {        // 32-byte atoms XOR-ed with (row & 3): logical 16-byte chunk of this physical one
+          const int cp = idx & 7, cl = ((((cp >> 1) ^ (row & 3)) << 1) | (cp & 1));
+          const float4 t = *reinterpret_cast<const float4*>(si + i0 + slab * 32 + cl * 4);
+          f.x *= t.x; f.y *= t.y; f.z *= t.z; f.w *= t.w;
+        }
       } else {                   // columns are reduction indices; logical 16-byte chunk = physical ^ (row & 7)
         const int c = (idx & 7) ^ (row & 7);
-        const float4 s = *reinterpret_cast<const float4*>(sc + r0 + c * 4);
-        x.x *= s.x; x.y *= s.y; x.z *= s.z; x.w *= s.w;
+        if (sc) f = *reinterpret_cast<const float4*>(sc + r0 + c * 4);
+        if (dual && si) { const float t = si[i0 + row]; f.x *= t; f.y *= t; f.z *= t; f.w *= t; }
+      }
+      if (dual) {
+        const float4 g = *p1;
+        x.x = fmaf(g.x, f.x, x.x); x.y = fmaf(g.y, f.y, x.y); x.z = fmaf(g.z, f.z, x.z); x.w = fmaf(g.w, f.w, x.w);
+      } else {
+        x.x *= f.x; x.y *= f.y; x.z *= f.z; x.w *= f.w;
       }
     }
     float4 h, l;
     split4(x, h, l);
     *p = h;
-    *reinterpret_cast<float4*>(part0 + o.part_bytes + ((size_t)idx << 4)) = l;
+    *p1 = l;
+  }
+}
+
+// Fast path for a 16 KB operand part (128 x 32 tile: every 3136 -> 512 weight tile): 4 chunks per converter thread,
+// fully unrolled.  With 256 threads striding by 256 chunks, a thread's row-within-slab (MN-major) / 16-byte column
+// (K-major) never changes, so the reduction-index factor is ONE load per stage and the row-index factors (si_*) are
+// loop invariants of the whole kernel (hoisted by the caller).
+struct ConvHoist { float4 si4[4]; float si1[4]; };
+__device__ __forceinline__ void convert_hoist(const UmOperand& o, int i0, int i_limit, int ct, ConvHoist& h) {
+  const float* __restrict__ si = o.convert == 2 ? o.scale_i : nullptr;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h.si4[j] = make_float4(1.f, 1.f, 1.f, 1.f);
+    h.si1[j] = 1.f;
+    if (si) {
+      if (o.mn_major) {   // slab j, logical 16-byte chunk cl of the 32-byte-atom swizzle
+        const int cp = ct & 7, row = ct >> 3, cl = ((((cp >> 1) ^ (row & 3)) << 1) | (cp & 1));
+        const int i = min(i0 + j * 32 + cl * 4, i_limit - 4);
+        h.si4[j] = *reinterpret_cast<const float4*>(si + i);
+      } else {
+        h.si1[j] = si[min(i0 + (ct >> 3) + j * 32, i_limit - 1)];
+      }
+    }
+  }
+}
+__device__ __forceinline__ void convert_part16k(const UmOperand& o, uint8_t* part0, int r0, int ct, const ConvHoist& h) {
+  const float* __restrict__ sc = o.scale_r;
+  const bool dual = o.convert == 2;
+  float4 fr = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (sc) {
+    if (o.mn_major) { const float s = sc[r0 + (ct >> 3)]; fr = make_float4(s, s, s, s); }
+    else fr = *reinterpret_cast<const float4*>(sc + r0 + (((ct & 7) ^ ((ct >> 3) & 7)) << 2));
+  }
+  float4 x[4], g[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    x[j] = *reinterpret_cast<const float4*>(part0 + ((size_t)(ct + j * 256) << 4));
+    if (dual) g[j] = *reinterpret_cast<const float4*>(part0 + 16384 + ((size_t)(ct + j * 256) << 4));
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float4 f = fr;
+    if (o.mn_major) { f.x *= h.si4[j].x; f.y *= h.si4[j].y; f.z *= h.si4[j].z; f.w *= h.si4[j].w; }
+    else { f.x *= h.si1[j]; f.y *= h.si1[j]; f.z *= h.si1[j]; f.w *= h.si1[j]; }
+    float4 v = x[j];
+    if (dual) { v.x = fmaf(g[j].x, f.x, v.x); v.y = fmaf(g[j].y, f.y, v.y); v.z = fmaf(g[j].z, f.z, v.z); v.w = fmaf(g[j].w, f.w, v.w); }
+    else if (sc) { v.x *= f.x; v.y *= f.y; v.z *= f.z; v.w *= f.w; }
+    float4 hh, ll;
+    split4(v, hh, ll);
+    *reinterpret_cast<float4*>(part0 + ((size_t)(ct + j * 256) << 4)) = hh;
+    *reinterpret_cast<float4*>(part0 + 16384 + ((size_t)(ct + j * 256) << 4)) = ll;
   }
 }
 
@@ -413,10 +482,14 @@ __global__ void __launch_bounds__(kThreadsU, 1)
     uint32_t ph = 0;
     uint8_t* st = stage_base;
     dz::pdl_enter();
+    const bool fast_a = conv_a && oa.part_bytes == 16384u && (!oa.mn_major || oa.lbo == 4096u);
+    ConvHoist hoist;
+    if (fast_a) convert_hoist(oa, cta.i0, p.MI, ct, hoist);
     for (int it = 0; it < nst; ++it) {
       mbar_wait(&full[s], ph);
-      if (conv_a) convert_part(oa, st, r0, ct);
-      if (conv_b) convert_part(ob, st + a_bytes, r0, ct);
+      if (fast_a) convert_part16k(oa, st, r0, ct, hoist);
+      else if (conv_a) convert_part(oa, st, r0, cta.i0, ct);
+      if (conv_b) convert_part(ob, st + a_bytes, r0, 0, ct);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&ready[s]);

@@ -36,7 +36,7 @@ struct UmNet {
   unsigned int* wg_ticket;                 // [4]
   int conv1_stag_bytes, conv1_tiles_per_pass;
   // noise-dependent problem fields (patched when the caller's noise buffer moves)
-  struct Patch { int prob; int field; int64_t off; };   // field 0: A.scale_r, 1: scale_i
+  struct Patch { int prob; int field; int64_t off; };   // field 0: A.scale_r, 2: A.scale_i, 1: scale_i (epilogue)
   std::vector<Patch> patches;
   const float* noise_cached = nullptr;
   std::string trace_tag;                   // debug: the launch with this tag writes CTA 0's clock stamps to trace_ptr
@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(kThreadsU, 1) conv1_wgrad_umma_kernel(const __
 // Finish kernels of the split FC GEMMs
 // ------------------------------------------------------------------------------------------------
 
-// h1[pass][stream][m][n] = relu( sum_s Pmu + b_mu[n] + eps_out[n] * (sum_s Psigma + b_sigma[n]) )   (networks.py:160-178)
+// h1[pass][stream][m][n] = relu( sum_s P + b_mu[n] + eps_out[n] * b_sigma[n] )   (networks.py:160-178; P already holds x(Wmu + Wsigma*noise))
 struct FcFinishArgs {
   const float* part; int S, B, nstream, noisy, npass;
   const float* bmu[3][2]; const float* bsig[3][2]; const float* eps_out[3][2];
@@ -587,10 +587,8 @@ __global__ void __launch_bounds__(256) um_fc_finish_kernel(const __grid_constant
   dz::pdl_enter();
   const int ps = blockIdx.y, pass = ps / a.nstream, st = ps - pass * a.nstream;
   const int total4 = a.B * 128;
-  const int q = a.noisy ? 2 : 1;
   const long long pstride = (long long)a.B * 512;
-  const float* pm = a.part + (long long)(ps * q) * a.S * pstride;
-  const float* psg = pm + (long long)a.S * pstride;
+  const float* pm = a.part + (long long)ps * a.S * pstride;
   for (int i4 = blockIdx.x * 256 + threadIdx.x; i4 < total4; i4 += gridDim.x * 256) {
     const int i = i4 << 2, n = i & 511;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -600,16 +598,10 @@ __global__ void __launch_bounds__(256) um_fc_finish_kernel(const __grid_constant
     }
     const float4 b = *reinterpret_cast<const float4*>(a.bmu[pass][st] + n);
     v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-    if (a.noisy) {
-      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int s = 0; s < a.S; ++s) {
-        const float4 x = *reinterpret_cast<const float4*>(psg + s * pstride + i);
-        g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
-      }
+    if (a.noisy) {     // the weights' noise went into the GEMM operand; the bias noise is b_sigma * eps_out (networks.py:172-177)
       const float4 bs = *reinterpret_cast<const float4*>(a.bsig[pass][st] + n);
       const float4 eo = *reinterpret_cast<const float4*>(a.eps_out[pass][st] + n);
-      v.x = fmaf(g.x + bs.x, eo.x, v.x); v.y = fmaf(g.y + bs.y, eo.y, v.y);
-      v.z = fmaf(g.z + bs.z, eo.z, v.z); v.w = fmaf(g.w + bs.w, eo.w, v.w);
+      v.x = fmaf(bs.x, eo.x, v.x); v.y = fmaf(bs.y, eo.y, v.y); v.z = fmaf(bs.z, eo.z, v.z); v.w = fmaf(bs.w, eo.w, v.w);
     }
     v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
     *reinterpret_cast<float4*>(a.h1 + (long long)ps * pstride + i) = v;
@@ -715,6 +707,18 @@ __global__ void __launch_bounds__(256) um_wgrad_finish_kernel(const __grid_const
   }
 }
 
+// L2 prefetch of the 3136 -> 512 weight matrices (both parameter sets): issued on the side stream at the start of the
+// step, while the sampler and the conv stack keep HBM idle, so that the weight-streaming GEMM later reads L2, not DRAM.
+struct PrefetchArgs { const float* ptr[8]; long long lines[8]; int n; };
+__global__ void __launch_bounds__(256) um_prefetch_kernel(const __grid_constant__ PrefetchArgs a) {
+  dz::pdl_enter();
+  for (int t = 0; t < a.n; ++t) {
+    const char* base = reinterpret_cast<const char*>(a.ptr[t]);
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < a.lines[t]; i += (long long)gridDim.x * 256)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + i * 128));
+  }
+}
+
 }  // namespace
 
 int um_split(const float* x, float* hi, float* lo, long long n, void* stream);   // dz_umma.cu
@@ -803,9 +807,8 @@ int64_t carve_net(UmNet* n, char* base) {
   n->h1_buf = nullptr; n->dh1_f32 = n->dh1_hi = n->dh1_lo = nullptr; n->fc_part = n->fcd_part = nullptr;
   n->fc_nprob = n->fcd_nsrc = 0; n->fc_splits = n->fcd_splits = 1;
   if (d.use_fc) {
-    const int q = d.noisy ? 2 : 1;
-    n->fc_nprob = d.npass * d.nstream * q;
-    n->fcd_nsrc = d.nstream * q;
+    n->fc_nprob = d.npass * d.nstream;      // noisy layers: mu and sigma are combined in the converter (one GEMM per stream)
+    n->fcd_nsrc = d.nstream;
     n->fc_splits = fc_splits_for(n->fc_nprob, g.feat / 32);
     const int ktiles = (g.feat + 127) / 128;
     n->fcd_splits = std::max(1, std::min(148 / (n->fcd_nsrc * ktiles), 8));
@@ -1183,13 +1186,25 @@ int build_plan(UmNet* n) {
     }
     // weight maps: [blob][stream][sigma] x {forward box (32 n, 32 k), gradient box (32 n, 128 k)}
     int m_wf_fc[2][2][2], m_wd_fc[2][2];
+    bool wf3d = true;
     for (int blob = 0; blob < 2; ++blob)
       for (int s = 0; s < d.nstream; ++s)
         for (int sg = 0; sg < q; ++sg) {
           const float* w = (blob ? d.target : d.online) + (sg ? d.off_fc_sw[s] : d.off_fc_w[s]);
           uint64_t dims[2] = {512, (uint64_t)feat}, strides[1] = {2048};
-          uint32_t box[2] = {32, 32};
-          m_wf_fc[blob][s][sg] = pl.add_map(w, 2, dims, strides, box, true);   // MN-major A operand (rows of W are the reduction)
+          // MN-major A operand (rows of W are the reduction): W[k][n] viewed as (n % 32, k, n / 32) so that ONE box of
+          // (32, 32, 4) lands as the four [32 k][32 n] slabs of a 128-column tile, slab-major — one TMA op per 16 KB tile
+          uint64_t dims3[3] = {32, (uint64_t)feat, 16}, strides3[2] = {2048, 128};
+          uint32_t box3[3] = {32, 32, 4};
+          if (wf3d) {
+            m_wf_fc[blob][s][sg] = pl.add_map(w, 3, dims3, strides3, box3, true);
+            if (m_wf_fc[blob][s][sg] < 0) wf3d = false;      // driver refused the permuted view: one op per slab instead
+          }
+          if (!wf3d) {
+            if (blob || s || sg) return fail(DZ_EINVAL, "fc weight tensor maps: inconsistent encodings");
+            uint32_t box2[2] = {32, 32};
+            m_wf_fc[blob][s][sg] = pl.add_map(w, 2, dims, strides, box2, true);
+          }
           if (m_wf_fc[blob][s][sg] < 0) return DZ_EINVAL;
           if (blob == 0) {
             uint32_t boxd[2] = {32, 128};
@@ -1197,7 +1212,7 @@ int build_plan(UmNet* n) {
             if (m_wd_fc[s][sg] < 0) return DZ_EINVAL;
           }
         }
-    // ---- forward: D[n, m] = sum_k W[k][n] x[m][k]
+    // ---- forward: D[n, m] = sum_k W[k][n] x[m][k];  noisy: W = Wmu + Wsigma * (eps_in[k] * eps_out[n]) formed by the converters
     {
       UmOperand Bo = um_kmajor(njt, true, false);
       const int nk = feat / 32, S = n->fc_splits, per = (nk + S - 1) / S;
@@ -1206,73 +1221,82 @@ int build_plan(UmNet* n) {
       n->l_fc.stages = std::min<int>(kStagesMax, (int)((226 * 1024 - 1024 - kCtlBytes) / n->l_fc.stage_bytes));
       for (int p = 0; p < d.npass; ++p) {
         const int blob = d.pass_target[p] ? 1 : 0;
-        for (int s = 0; s < d.nstream; ++s)
-          for (int sg = 0; sg < q; ++sg) {
-            const int qi = (p * d.nstream + s) * q + sg;
-            UmProblem pr;
-            memset(&pr, 0, sizeof(pr));
-            pr.A = um_mnmajor(128, 32, true, nullptr); pr.B = Bo; pr.ksteps = 4; pr.run_stages = 1; pr.red_per_stage = 32;
-            pr.epi = UM_EPI_PARTIAL; pr.MI = 512; pr.NJ = B;
-            pr.C = n->fc_part + (int64_t)qi * S * B * 512; pr.sc_i = 1; pr.sc_j = 512; pr.split_stride = (long long)B * 512;
-            const int prob = (int)pl.probs.size();
-            pl.probs.push_back(pr);
-            if (sg) n->patches.push_back({prob, 0, (int64_t)d.noise_apply[p] * d.noise_stride + d.noise_off_in[s]});
-            for (int nt = 0; nt < 4; ++nt)
-              for (int sp = 0; sp < S; ++sp) {
-                const int k0 = sp * per, k1 = std::min(nk, k0 + per);
-                if (k1 <= k0) continue;
-                UmCta c;
-                memset(&c, 0, sizeof(c));
-                c.prob = (uint32_t)prob; c.op0 = (uint32_t)pl.ops.size(); c.nstages = (uint32_t)(k1 - k0); c.ops_per_stage = 6;
-                c.tx_bytes = (uint32_t)(16384 + 2 * njt * 128);
-                c.r0 = 32 * k0; c.i0 = nt * 128; c.split = sp;
-                for (int ks = k0; ks < k1; ++ks) {
-                  for (int sl = 0; sl < 4; ++sl) push_op(pl, m_wf_fc[blob][s][sg], sl * 4096, nt * 128 + 32 * sl, 32 * ks, 0, 0, 0);
-                  for (int part = 0; part < 2; ++part) push_op(pl, m_x[part], 32768 + part * Bo.part_bytes, 32 * ks, p * B, 0, 0, 0);
-                }
-                pl.ctas.push_back(c);
-              }
+        for (int s = 0; s < d.nstream; ++s) {
+          const int qi = p * d.nstream + s;
+          UmProblem pr;
+          memset(&pr, 0, sizeof(pr));
+          pr.A = um_mnmajor(128, 32, true, nullptr); pr.B = Bo; pr.ksteps = 4; pr.run_stages = 1; pr.red_per_stage = 32;
+          if (d.noisy) pr.A.convert = 2;
+          pr.epi = UM_EPI_PARTIAL; pr.MI = 512; pr.NJ = B;
+          pr.C = n->fc_part + (int64_t)qi * S * B * 512; pr.sc_i = 1; pr.sc_j = 512; pr.split_stride = (long long)B * 512;
+          const int prob = (int)pl.probs.size();
+          pl.probs.push_back(pr);
+          if (d.noisy) {
+            n->patches.push_back({prob, 0, (int64_t)d.noise_apply[p] * d.noise_stride + d.noise_off_in[s]});
+            n->patches.push_back({prob, 2, (int64_t)d.noise_apply[p] * d.noise_stride + d.noise_off_out[s]});
           }
+          // the four 128-column tiles of one k range sit in neighbouring CTAs: together they stream whole 2 KB rows of W
+          for (int sp = 0; sp < S; ++sp)
+            for (int nt = 0; nt < 4; ++nt) {
+              const int k0 = sp * per, k1 = std::min(nk, k0 + per);
+              if (k1 <= k0) continue;
+              UmCta c;
+              memset(&c, 0, sizeof(c));
+              c.prob = (uint32_t)prob; c.op0 = (uint32_t)pl.ops.size(); c.nstages = (uint32_t)(k1 - k0);
+              c.ops_per_stage = (wf3d ? 1 : 4) * (d.noisy ? 2 : 1) + 2;
+              c.tx_bytes = (uint32_t)((d.noisy ? 32768 : 16384) + 2 * njt * 128);
+              c.r0 = 32 * k0; c.i0 = nt * 128; c.split = sp;
+              for (int ks = k0; ks < k1; ++ks) {
+                for (int sg = 0; sg < (d.noisy ? 2 : 1); ++sg) {
+                  if (wf3d) push_op(pl, m_wf_fc[blob][s][sg], sg * 16384, 0, 32 * ks, nt * 4, 0, 0);
+                  else for (int sl = 0; sl < 4; ++sl) push_op(pl, m_wf_fc[blob][s][sg], sg * 16384 + sl * 4096, nt * 128 + 32 * sl, 32 * ks, 0, 0, 0);
+                }
+                for (int part = 0; part < 2; ++part) push_op(pl, m_x[part], 32768 + part * Bo.part_bytes, 32 * ks, p * B, 0, 0, 0);
+              }
+              pl.ctas.push_back(c);
+            }
+        }
       }
       n->l_fc.nctas = (int)pl.ctas.size() - n->l_fc.cta0;
     }
-    // ---- input gradient: D[k, m] = sum_n W[k][n] g[m][n]   (sigma: W * eps_out[n] in the converter, * eps_in[k] in the epilogue)
+    // ---- input gradient: D[k, m] = sum_n W[k][n] g[m][n];  noisy: W = Wmu + Wsigma * (eps_in[k] * eps_out[n]) in the converters
     {
       UmOperand Bo = um_kmajor(njt, true, false);
       const int S = n->fcd_splits, per = (16 + S - 1) / S, ktiles = (feat + 127) / 128;
       n->l_fcd.cta0 = (int)pl.ctas.size(); n->l_fcd.njt = njt; n->l_fcd.convert = true;
       n->l_fcd.stage_bytes = 2 * 16384 + 2 * Bo.part_bytes;
       n->l_fcd.stages = std::min<int>(kStagesMax, (int)((226 * 1024 - 1024 - kCtlBytes) / n->l_fcd.stage_bytes));
-      for (int s = 0; s < d.nstream; ++s)
-        for (int sg = 0; sg < q; ++sg) {
-          const int src = s * q + sg;
-          UmProblem pr;
-          memset(&pr, 0, sizeof(pr));
-          pr.A = um_kmajor(128, true, true, nullptr); pr.B = Bo; pr.ksteps = 4; pr.run_stages = 2; pr.red_per_stage = 32;
-          pr.epi = UM_EPI_PARTIAL; pr.MI = feat; pr.NJ = B;
-          pr.C = n->fcd_part + (int64_t)src * S * B * feat; pr.sc_i = 1; pr.sc_j = feat; pr.split_stride = (long long)B * feat;
-          const int prob = (int)pl.probs.size();
-          pl.probs.push_back(pr);
-          if (sg) {
-            n->patches.push_back({prob, 0, (int64_t)d.noise_apply[0] * d.noise_stride + d.noise_off_out[s]});
-            n->patches.push_back({prob, 1, (int64_t)d.noise_apply[0] * d.noise_stride + d.noise_off_in[s]});
-          }
-          for (int kt = 0; kt < ktiles; ++kt)
-            for (int sp = 0; sp < S; ++sp) {
-              const int n0 = sp * per, n1 = std::min(16, n0 + per);
-              if (n1 <= n0) continue;
-              UmCta c;
-              memset(&c, 0, sizeof(c));
-              c.prob = (uint32_t)prob; c.op0 = (uint32_t)pl.ops.size(); c.nstages = (uint32_t)(n1 - n0); c.ops_per_stage = 3;
-              c.tx_bytes = (uint32_t)(16384 + 2 * njt * 128);
-              c.r0 = 32 * n0; c.i0 = kt * 128; c.split = sp;
-              for (int ns = n0; ns < n1; ++ns) {
-                push_op(pl, m_wd_fc[s][sg], 0, 32 * ns, kt * 128, 0, 0, 0);
-                for (int part = 0; part < 2; ++part) push_op(pl, m_g[part], 32768 + part * Bo.part_bytes, 32 * ns, s * B, 0, 0, 0);
-              }
-              pl.ctas.push_back(c);
-            }
+      for (int s = 0; s < d.nstream; ++s) {
+        UmProblem pr;
+        memset(&pr, 0, sizeof(pr));
+        pr.A = um_kmajor(128, true, true, nullptr); pr.B = Bo; pr.ksteps = 4; pr.run_stages = 2; pr.red_per_stage = 32;
+        if (d.noisy) pr.A.convert = 2;
+        pr.epi = UM_EPI_PARTIAL; pr.MI = feat; pr.NJ = B;
+        pr.C = n->fcd_part + (int64_t)s * S * B * feat; pr.sc_i = 1; pr.sc_j = feat; pr.split_stride = (long long)B * feat;
+        const int prob = (int)pl.probs.size();
+        pl.probs.push_back(pr);
+        if (d.noisy) {
+          n->patches.push_back({prob, 0, (int64_t)d.noise_apply[0] * d.noise_stride + d.noise_off_out[s]});
+          n->patches.push_back({prob, 2, (int64_t)d.noise_apply[0] * d.noise_stride + d.noise_off_in[s]});
         }
+        for (int kt = 0; kt < ktiles; ++kt)
+          for (int sp = 0; sp < S; ++sp) {
+            const int n0 = sp * per, n1 = std::min(16, n0 + per);
+            if (n1 <= n0) continue;
+            UmCta c;
+            memset(&c, 0, sizeof(c));
+            c.prob = (uint32_t)prob; c.op0 = (uint32_t)pl.ops.size(); c.nstages = (uint32_t)(n1 - n0);
+            c.ops_per_stage = d.noisy ? 4 : 3;
+            c.tx_bytes = (uint32_t)((d.noisy ? 32768 : 16384) + 2 * njt * 128);
+            c.r0 = 32 * n0; c.i0 = kt * 128; c.split = sp;
+            for (int ns = n0; ns < n1; ++ns) {
+              push_op(pl, m_wd_fc[s][0], 0, 32 * ns, kt * 128, 0, 0, 0);
+              if (d.noisy) push_op(pl, m_wd_fc[s][1], 16384, 32 * ns, kt * 128, 0, 0, 0);
+              for (int part = 0; part < 2; ++part) push_op(pl, m_g[part], 32768 + part * Bo.part_bytes, 32 * ns, s * B, 0, 0, 0);
+            }
+            pl.ctas.push_back(c);
+          }
+      }
       n->l_fcd.nctas = (int)pl.ctas.size() - n->l_fcd.cta0;
     }
   }
@@ -1286,7 +1310,7 @@ int apply_noise(UmNet* n, const float* noise, void* stream) {
   if (cs != cudaStreamCaptureStatusNone) return fail(DZ_EINVAL, "the noise buffer must not move between graph captures (keep one buffer per learner)");
   for (const auto& p : n->patches) {
     UmProblem& pr = n->plan.probs[p.prob];
-    if (p.field == 0) pr.A.scale_r = noise + p.off; else pr.scale_i = noise + p.off;
+    if (p.field == 0) pr.A.scale_r = noise + p.off; else if (p.field == 2) pr.A.scale_i = noise + p.off; else pr.scale_i = noise + p.off;
   }
   DZ_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
   DZ_CUDA_OK(cudaMemcpy(n->plan.d_probs, n->plan.probs.data(), n->plan.probs.size() * sizeof(UmProblem), cudaMemcpyHostToDevice));
@@ -1375,6 +1399,22 @@ int um_pack_weights(UmNet* n, void* stream) {
   a.wd3_hi = n->wd3_hi; a.wd3_lo = n->wd3_lo; a.wd2_hi = n->wd2_hi; a.wd2_lo = n->wd2_lo;
   const int total = 2 * 77824 + 64 * 576 + 128 * 256;
   DZ_LAUNCH_NAMED("conv_pack", um_pack_conv_kernel, (unsigned)ceil_div(total, 256), 256, 0, stream, a);
+  return DZ_OK;
+}
+
+int um_prefetch_fc(UmNet* n, void* stream) {
+  const UmNetDesc& d = n->d;
+  if (!d.use_fc) return DZ_OK;
+  PrefetchArgs a;
+  memset(&a, 0, sizeof(a));
+  const long long lines = ((long long)n->feat * 512 * 4 + 127) / 128;
+  for (int blob = 0; blob < 2; ++blob)
+    for (int s = 0; s < d.nstream; ++s)
+      for (int sg = 0; sg < (d.noisy ? 2 : 1); ++sg) {
+        a.ptr[a.n] = (blob ? d.target : d.online) + (sg ? d.off_fc_sw[s] : d.off_fc_w[s]);
+        a.lines[a.n++] = lines;
+      }
+  DZ_LAUNCH_NAMED("fc_prefetch", um_prefetch_kernel, 148 * 4, 256, 0, stream, a);
   return DZ_OK;
 }
 

@@ -271,9 +271,11 @@ class Learner:
     _lib.call('dz_learner_update', self._h, C.byref(batch), C.byref(out), 1 if apply_update else 0, _cstream())
     self._keep = (keep, w)
 
-  def generate_randomness(self, seed: int) -> None:
-    """Fills `.taus` / `.noise` for the next update from the device generator (Philox)."""
-    _lib.call('dz_learner_generate_randomness', self._h, seed, self.taus.data_ptr(), self.noise.data_ptr(), _cstream())
+  def generate_randomness(self, seed: int, beside_sampler: bool = False) -> None:
+    """Fills `.taus` / `.noise` for the next update from the device generator (Philox).  `beside_sampler`: enqueue on
+    the learner's side stream (ordered before the next learn()/update()/q_values() only)."""
+    _lib.call('dz_learner_generate_randomness_async' if beside_sampler else 'dz_learner_generate_randomness', self._h, seed,
+              self.taus.data_ptr(), self.noise.data_ptr(), _cstream())
 
   def q_values(self, obs_u8: torch.Tensor, taus=None, noise=None) -> torch.Tensor:
     """Online-network Q-values for one observation (the network half of select_action)."""

@@ -277,6 +277,10 @@ int dz_learner_learn(dz_learner* l, const dz_replay_view* replay, int32_t priori
  * `seed`, counter d_counters[1] which it advances): taus ~ U[0,1) (iqn/agent.py:45-50); noise =
  * sign(n)*sqrt(|n|), n ~ TruncNormal(-2,2) (networks.py:142-144).  NOT the JAX threefry stream. */
 int dz_learner_generate_randomness(dz_learner* l, uint64_t seed, float* d_taus, float* d_noise, void* stream);
+/* Same draws, enqueued on the learner's side stream: ordered after the work already on `stream` and before the next
+ * dz_learner_learn / dz_learner_update / dz_learner_q_values on `stream` (they run beside the sampler instead of in
+ * front of it).  Any other reader of d_taus / d_noise must synchronise the device first. */
+int dz_learner_generate_randomness_async(dz_learner* l, uint64_t seed, float* d_taus, float* d_noise, void* stream);
 
 /* select_action's network part (dqn/agent.py:121-131; rainbow/agent.py:125-133; iqn/agent.py:228-243):
  * online forward on ONE observation -> q_values[num_actions] on device.  The epsilon-greedy draw stays on the host. */
