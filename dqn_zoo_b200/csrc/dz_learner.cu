@@ -825,8 +825,11 @@ __global__ void __launch_bounds__(128) q_values_kernel(int kind, int A, int atom
 
 // Sum of squares -> per-block partials; the last block to finish adds them in a fixed order
 // (deterministic), publishes the global norm and bumps the optimizer step count.
+// sumsq_only: norm_out[0] receives the SUM OF SQUARES of the range (the split global norm: the optimizer adds the
+// conv-gradient partials written by the weight-gradient finish kernels and takes the root), user_norm is not written.
 __global__ void __launch_bounds__(256) grad_norm_kernel(const float* __restrict__ g, long long n, float* partials,
-                                                        unsigned int* ticket, float* norm_out, int64_t* counters, float* user_norm) {
+                                                        unsigned int* ticket, float* norm_out, int64_t* counters, float* user_norm,
+                                                        int sumsq_only) {
   dz::pdl_enter();
   __shared__ float s[32];
   __shared__ bool last;
@@ -860,8 +863,8 @@ __global__ void __launch_bounds__(256) grad_norm_kernel(const float* __restrict_
     if (threadIdx.x == 0) {
       float tot = 0.f;
       for (int i = 0; i < (blockDim.x >> 5); ++i) tot += s[i];
-      norm_out[0] = sqrtf(tot);
-      if (user_norm) user_norm[0] = norm_out[0];
+      norm_out[0] = sumsq_only ? tot : sqrtf(tot);
+      if (user_norm && !sumsq_only) user_norm[0] = norm_out[0];
       *ticket = 0;
       counters[0] += 1;  // optax adam `count` (also counts rmsprop steps)
     }
@@ -871,7 +874,30 @@ __global__ void __launch_bounds__(256) grad_norm_kernel(const float* __restrict_
 struct OptArgs {
   int kind; float lr, eps, decay, b1, b2, max_norm;
   float* p; const float* g; float* m; float* v; long long n; const float* norm; const int64_t* counters;
+  // split global norm (tcgen05 path): norm = sqrt(fc_sumsq[0] + sum of parts[0..nparts)), recomputed identically by every block
+  const float* parts; int nparts; const float* fc_sumsq; float* norm_out; float* user_norm;
 };
+
+// Fixed-order block reduction of the split-norm partials: every block of every launch gets the same bits.
+__device__ __forceinline__ float split_norm(const float* __restrict__ parts, int nparts, const float* __restrict__ fc_sumsq) {
+  __shared__ float s_red[8];
+  float t = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += 256) t += __ldcg(parts + i);
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  float tot = __ldcg(fc_sumsq);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += s_red[i];
+  return sqrtf(tot);
+}
+
+__global__ void __launch_bounds__(256) norm_finalize_kernel(const float* parts, int nparts, const float* fc_sumsq, float* norm_out,
+                                                            float* user_norm) {
+  dz::pdl_enter();
+  const float norm = split_norm(parts, nparts, fc_sumsq);
+  if (threadIdx.x == 0) { norm_out[0] = norm; if (user_norm) user_norm[0] = norm; }
+}
 
 // One parameter.  optax.scale_by_adam divides the moments by (1 - b^t) per element; here the two
 // reciprocals are formed once per thread and multiplied in (<= 1 ulp from the division), leaving one sqrt
@@ -903,14 +929,6 @@ __device__ __forceinline__ float opt_one(const OptArgs& o, float p, float g, flo
 template <int KIND>
 __global__ void __launch_bounds__(256) optimizer_kernel(OptArgs o) {
   dz::pdl_enter();
-  const float norm = o.norm[0];
-  const bool clip = o.max_norm > 0.f && !(norm < o.max_norm);  // optax.clip_by_global_norm trigger
-  float c1 = 1.f, c2 = 1.f;
-  if (KIND == DZ_ADAM) {
-    float t = (float)o.counters[0];
-    c1 = 1.0f / (1.0f - powf(o.b1, t));
-    c2 = 1.0f / (1.0f - powf(o.b2, t));
-  }
   const long long n4 = o.n >> 2;
   float4* p4 = reinterpret_cast<float4*>(o.p);
   const float4* g4 = reinterpret_cast<const float4*>(o.g);
@@ -918,12 +936,36 @@ __global__ void __launch_bounds__(256) optimizer_kernel(OptArgs o) {
   float4* v4 = reinterpret_cast<float4*>(o.v);
   constexpr int U = 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < n4; i0 += stride * U) {
-    float4 p[U], g[U], m[U], v[U];
+  const long long first = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  // the first batch of loads is issued BEFORE the norm is formed: the split-norm reduction (shared memory, a block
+  // barrier, ~700 L2 reads per block) then hides behind the memory latency of the stream instead of preceding it
+  float4 p[U], g[U], m[U], v[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      long long i = i0 + u * stride;
-      if (i < n4) { p[u] = p4[i]; g[u] = g4[i]; m[u] = m4[i]; v[u] = v4[i]; }
+  for (int u = 0; u < U; ++u) {
+    long long i = first + u * stride;
+    if (i < n4) { p[u] = p4[i]; g[u] = g4[i]; m[u] = m4[i]; v[u] = v4[i]; }
+  }
+  float norm;
+  if (o.parts != nullptr) {
+    norm = split_norm(o.parts, o.nparts, o.fc_sumsq);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { o.norm_out[0] = norm; if (o.user_norm) o.user_norm[0] = norm; }
+  } else {
+    norm = o.norm[0];
+  }
+  const bool clip = o.max_norm > 0.f && !(norm < o.max_norm);  // optax.clip_by_global_norm trigger
+  float c1 = 1.f, c2 = 1.f;
+  if (KIND == DZ_ADAM) {
+    float t = (float)o.counters[0];
+    c1 = 1.0f / (1.0f - powf(o.b1, t));
+    c2 = 1.0f / (1.0f - powf(o.b2, t));
+  }
+  for (long long i0 = first; i0 < n4; i0 += stride * U) {
+    if (i0 != first) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        long long i = i0 + u * stride;
+        if (i < n4) { p[u] = p4[i]; g[u] = g4[i]; m[u] = m4[i]; v[u] = v4[i]; }
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -991,6 +1033,11 @@ struct dz_learner {
   cudaStream_t side;
   cudaEvent_t ev_fork, ev_join;
   bool side_dirty;
+  // third branch: the FC part of the split gradient norm and the conv2 weight gradient run beside the first side stream
+  cudaStream_t side2;
+  cudaEvent_t ev_fork2, ev_join2;
+  bool side2_dirty;
+  float* norm_parts;                        // split-norm slots written by the conv weight-gradient finish kernels
   // TMA-fed tcgen05 path of the batch-sized step (dz_umma_net.cu): torso + 3136 -> 512 layer(s), forward and input gradients
   UmNet* um;
   char* um_ws;
@@ -1122,6 +1169,7 @@ int64_t carve(dz_learner* l, char* base) {
   l->s_d = w.take<float>(B);
   l->s_w = w.take<float>(B);
   l->q_scratch = w.take<float>(64);
+  l->norm_parts = w.take<float>(1024);
   l->um_ws = nullptr;
   if (g_umma) {
     UmNetDesc ud = make_um_desc(l);
@@ -1805,6 +1853,22 @@ int join_side(dz_learner* l, void* stream) {
   l->side_dirty = false;
   return DZ_OK;
 }
+// Second side stream: `from` is the stream whose enqueued work it must wait for (the main stream or the first side stream).
+void* fork_side2(dz_learner* l, void* from, void* fallback) {
+  if (!l->side2) return fallback;
+  if (cudaEventRecord(l->ev_fork2, (cudaStream_t)from) != cudaSuccess) return fallback;
+  if (cudaStreamWaitEvent(l->side2, l->ev_fork2, 0) != cudaSuccess) return fallback;
+  l->side2_dirty = true;
+  return l->side2;
+}
+int join_side2(dz_learner* l, void* stream) {
+  if (!l->side2 || !l->side2_dirty) return DZ_OK;
+  DZ_CUDA_OK(cudaEventRecord(l->ev_join2, l->side2));
+  DZ_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, l->ev_join2, 0));
+  l->side2_dirty = false;
+  return DZ_OK;
+}
+bool split_norm_active(const dz_learner* l);
 
 // Torso backward from dact3 (already masked by act3 > 0): conv3/conv2/conv1 weight+bias grads.
 int backward_torso(dz_learner* l, const uint8_t* const* rows0, void* stream) {
@@ -1818,8 +1882,11 @@ int backward_torso(dz_learner* l, const uint8_t* const* rows0, void* stream) {
   GemmBatch gb;
   if (l->um && l->cfg.kind == DZ_IQN) DZ_TRY(um_split_dact3(l->um, stream));   // dact3 came from the Hadamard kernel (fp32)
   // conv3 wgrad
-  if (l->um) {
-    DZ_TRY(um_wgrad_conv3(l->um, fork_side(l, stream)));
+  float* norm_parts = split_norm_active(l) ? l->norm_parts : nullptr;
+  if (l->um) {   // conv3 weight gradient + its finish (partial sums, bias gradient, split-norm partials) on the side stream
+    void* ws = fork_side(l, stream);
+    DZ_TRY(um_wgrad_conv3(l->um, ws));
+    DZ_TRY(um_wgrad_finish_layer(l->um, 3, G + L.off("conv3/w"), G + L.off("conv3/b"), norm_parts, ws));
   } else {
     GemmProblem p = zero_problem();
     set_conv(p, A_CONV_F32, l->act2[0], B, d.h2, d.w2, 64, 3, 3, 1);
@@ -1845,8 +1912,10 @@ int backward_torso(dz_learner* l, const uint8_t* const* rows0, void* stream) {
               d.h3, d.w3);
   }
   // conv2 wgrad
-  if (l->um) {
-    DZ_TRY(um_wgrad_conv2(l->um, fork_side(l, stream)));
+  if (l->um) {   // conv2: on the second side stream, beside conv3's (both fit next to the input-gradient kernels)
+    void* ws = l->side2 ? fork_side2(l, stream, stream) : fork_side(l, stream);
+    DZ_TRY(um_wgrad_conv2(l->um, ws));
+    DZ_TRY(um_wgrad_finish_layer(l->um, 2, G + L.off("conv2/w"), G + L.off("conv2/b"), norm_parts, ws));
   } else {
     GemmProblem p = zero_problem();
     set_conv(p, A_CONV_F32, l->act1[0], B, d.h1, d.w1, 32, 4, 4, 2);
@@ -1875,8 +1944,8 @@ int backward_torso(dz_learner* l, const uint8_t* const* rows0, void* stream) {
   if (l->um) {
     void* ws = fork_side(l, stream);
     DZ_TRY(um_wgrad_conv1(l->um, rows0, ws));
-    DZ_TRY(um_wgrad_finish(l->um, G + L.off("conv3/w"), G + L.off("conv3/b"), G + L.off("conv2/w"), G + L.off("conv2/b"),
-                           nullptr, 0, G + L.off("conv1/w"), G + L.off("conv1/b"), ws));
+    DZ_TRY(um_wgrad_finish_layer(l->um, 1, G + L.off("conv1/w"), G + L.off("conv1/b"), norm_parts, ws));
+    DZ_TRY(join_side2(l, stream));
     return join_side(l, stream);
   } else {
     GemmProblem p = zero_problem();
@@ -2137,15 +2206,36 @@ int backward_iqn(dz_learner* l, void* stream) {
   return DZ_OK;
 }
 
+// Split global norm (tcgen05 path, every agent but IQN): the sum of squares of everything behind the conv tensors is taken
+// on the second side stream as soon as the last FC / head weight gradient is written (norm_fc_range), the conv tensors'
+// partials come from the per-layer weight-gradient finish kernels, and the optimizer (or norm_finalize_kernel) combines them.
+bool split_norm_active(const dz_learner* l) { return l->um != nullptr && l->cfg.kind != DZ_IQN && l->side2 != nullptr; }
+
+int norm_fc_range(dz_learner* l, bool apply, void* stream) {
+  const long long begin = l->lay.off(l->cfg.kind == DZ_RAINBOW ? "adv1/mu/w" : "fc1/w");
+  const long long n = l->lay.total - begin;
+  DZ_LAUNCH(grad_norm_kernel, kNormBlocks, 256, 0, stream, l->buf.d_grads + begin, n, l->scalars + 8, l->ticket, l->scalars + 1,
+            apply ? l->buf.d_counters : l->buf.d_counters + 3, (float*)nullptr, 1);
+  return DZ_OK;
+}
+
 int run_optimizer(dz_learner* l, float* user_norm, bool apply, void* stream) {
   const dz_learner_config& c = l->cfg;
   long long n = l->lay.total;
   float* norm = l->scalars;
-  DZ_LAUNCH(grad_norm_kernel, kNormBlocks, 256, 0, stream, l->buf.d_grads, n, l->scalars + 8, l->ticket, norm,
-            apply ? l->buf.d_counters : l->buf.d_counters + 3, user_norm);
+  const bool split = split_norm_active(l);
+  const float* parts = split ? l->norm_parts : nullptr;
+  const int nparts = split ? um_norm_slots(l->um) : 0;
+  if (!split) {
+    DZ_LAUNCH(grad_norm_kernel, kNormBlocks, 256, 0, stream, l->buf.d_grads, n, l->scalars + 8, l->ticket, norm,
+              apply ? l->buf.d_counters : l->buf.d_counters + 3, user_norm, 0);
+  } else if (!apply) {
+    DZ_LAUNCH(norm_finalize_kernel, 1, 256, 0, stream, parts, nparts, l->scalars + 1, norm, user_norm);
+  }
   if (!apply) return DZ_OK;
   OptArgs o{c.optimizer, c.learning_rate, c.opt_eps, c.rms_decay, c.adam_b1, c.adam_b2, c.max_global_grad_norm,
-            l->buf.d_online, l->buf.d_grads, l->buf.d_opt_state, l->buf.d_opt_state + n, n, norm, l->buf.d_counters};
+            l->buf.d_online, l->buf.d_grads, l->buf.d_opt_state, l->buf.d_opt_state + n, n, norm, l->buf.d_counters,
+            parts, nparts, l->scalars + 1, norm, user_norm};
   static const int per_sm = getenv("DZ_OPT_BLOCKS") ? atoi(getenv("DZ_OPT_BLOCKS")) : 8;
   if (c.optimizer == DZ_ADAM) DZ_LAUNCH_NAMED("optimizer_kernel", optimizer_kernel<DZ_ADAM>, 148 * per_sm, 256, 0, stream, o);
   else DZ_LAUNCH_NAMED("optimizer_kernel", optimizer_kernel<DZ_RMSPROP_CENTERED>, 148 * per_sm, 256, 0, stream, o);
@@ -2243,9 +2333,14 @@ int update_impl(dz_learner* l, const dz_batch* batch, const dz_update_outputs* o
   if (c.kind == DZ_RAINBOW) DZ_TRY(backward_rainbow(l, batch->d_noise, stream));
   else if (c.kind == DZ_IQN) DZ_TRY(backward_iqn(l, stream));
   else DZ_TRY(backward_plain(l, stream));
+  if (split_norm_active(l)) {   // every gradient behind the conv tensors is final once the side stream's FC / head wgrads are done
+    void* from = l->side_dirty ? (void*)l->side : stream;
+    DZ_TRY(norm_fc_range(l, apply_update != 0, fork_side2(l, from, stream)));
+  }
   DZ_TRY(backward_torso(l, batch->d_s_tm1_rows, stream));
 
   // ---- clip_by_global_norm + adam / rmsprop + apply_updates
+  DZ_TRY(join_side2(l, stream));
   DZ_TRY(join_side(l, stream));
   DZ_TRY(run_optimizer(l, out->d_grad_norm, apply_update != 0, stream));
   return DZ_OK;
@@ -2323,11 +2418,18 @@ int dz_learner_create(const dz_learner_config* cfg, const dz_learner_buffers* bu
     l->dact3 = um_dact_f32(l->um, 3); l->dact2 = um_dact_f32(l->um, 2); l->dact1 = um_dact_f32(l->um, 1);
   }
   l->side = nullptr; l->ev_fork = nullptr; l->ev_join = nullptr; l->side_dirty = false;
+  l->side2 = nullptr; l->ev_fork2 = nullptr; l->ev_join2 = nullptr; l->side2_dirty = false;
   if (getenv("DZ_NO_SIDE_STREAM") == nullptr) {
     if (cudaStreamCreateWithFlags(&l->side, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&l->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&l->ev_join, cudaEventDisableTiming) != cudaSuccess) {
       l->side = nullptr;
+      cudaGetLastError();
+    }
+    if (l->side && (cudaStreamCreateWithFlags(&l->side2, cudaStreamNonBlocking) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&l->ev_fork2, cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&l->ev_join2, cudaEventDisableTiming) != cudaSuccess)) {
+      l->side2 = nullptr;
       cudaGetLastError();
     }
   }
@@ -2357,6 +2459,7 @@ void dz_learner_destroy(dz_learner* l) {
   if (!l) return;
   um_net_destroy(l->um);
   if (l->side) { cudaStreamSynchronize(l->side); cudaStreamDestroy(l->side); }
+  if (l->side2) { cudaStreamSynchronize(l->side2); cudaStreamDestroy(l->side2); }
   if (l->ev_fork) cudaEventDestroy(l->ev_fork);
   if (l->ev_join) cudaEventDestroy(l->ev_join);
   delete l;

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kThreadsP, EPI ? 2 : 1) tc_pgemm_kernel(const 
 
   if (warp == 0) {
     // ---------------------------------------------------------------- producer
-    if (lane == 0) {
+    if (elect_one()) {
       const float* a_hi = p.A.hi; const float* a_lo = p.A.lo; const float* b_hi = p.B.hi; const float* b_lo = p.B.lo;
       const long long a_rg = p.A.rg_total, b_rg = p.B.rg_total;
       for (int it = 0; it < nkb; ++it) {
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kThreadsP, EPI ? 2 : 1) tc_pgemm_kernel(const 
       }
       mbar_wait(&full[s], ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) {
+      if (elect_one()) {   // elect.sync: ptxas emits the MMAs back to back (no ELECT / BRA.U.ANY loop around each)
         const uint32_t st = smem_u32(stage_base + (size_t)s * L::kStage);
         const uint32_t a_hi = st, a_lo = st + L::kA, b_hi = st + 2 * L::kA, b_lo = st + 2 * L::kA + L::kB;
         const uint32_t d = tmem_base + (uint32_t)(buf * BNJ);

@@ -113,11 +113,25 @@ int UmPlan::launch(const char* tag, const UmLaunch& l, void* stream, long long* 
   if (l.nctas <= 0) return DZ_OK;
   if (!d_ctas) return fail(DZ_EINVAL, "umma plan not uploaded");
   if (l.stages < 1 || l.stages > um::kStagesMax || l.stage_bytes % 1024) return fail(DZ_EINVAL, "umma launch geometry");
+  for (int ci = l.cta0; ci < l.cta0 + l.nctas; ++ci) {
+    const UmProblem& pr = probs[ctas[ci].prob];
+    const uint32_t want = pr.B.mn_major ? (uint32_t)(l.njt / 32) * pr.B.lbo : (uint32_t)l.njt * 128u;
+    if (pr.A.nparts != 2 || pr.B.nparts != 2 || pr.B.part_bytes != want)
+      return fail(DZ_EINVAL, "umma launch: operands must be hi/lo pairs with the B parts adjacent (one descriptor spans both)");
+  }
   for (int ci = l.cta0; ci < l.cta0 + l.nctas; ++ci)
     if (ctas[ci].ops_per_stage > 32) return fail(DZ_EINVAL, "umma launch: more than 32 TMA ops per stage");
-  const size_t smem = 1024 + um::kCtlBytes + (size_t)l.stages * l.stage_bytes;
+  // two MMA-issuer warps need static slot ownership: stage count a multiple of 2 * run_stages (dz_umma.cuh)
+  int stages = l.stages;
+  {
+    uint32_t rs = 1;
+    for (int ci = l.cta0; ci < l.cta0 + l.nctas; ++ci) rs = std::max(rs, probs[ctas[ci].prob].run_stages);
+    const int rounded = (int)(l.stages / (2 * rs) * (2 * rs));
+    if (rounded >= (int)(2 * rs)) stages = rounded;
+  }
+  const size_t smem = 1024 + um::kCtlBytes + (size_t)stages * l.stage_bytes;
   if (smem > 227 * 1024) return fail(DZ_EINVAL, "umma launch needs too much shared memory");
-  if ((size_t)l.stages * l.stage_bytes < (size_t)128 * l.njt * 4) return fail(DZ_EINVAL, "umma launch: stage buffers smaller than the store-phase staging tile");
+  if ((size_t)stages * l.stage_bytes < (size_t)128 * l.njt * 4) return fail(DZ_EINVAL, "umma launch: stage buffers smaller than the store-phase staging tile");
   const int v = l.njt == 32 ? 0 : 1;
   if (l.njt != 32 && l.njt != 64) return fail(DZ_EINVAL, "umma launch: NJT must be 32 or 64");
   DZ_TRY_CFG(configure());
@@ -125,10 +139,10 @@ int UmPlan::launch(const char* tag, const UmLaunch& l, void* stream, long long* 
   for (int q = 0; q < l.nmaps; ++q) lm.m[q] = maps[l.map_ids[q]];
   for (int q = l.nmaps; q < um::kMaxMapsPerLaunch; ++q) lm.m[q] = maps[l.map_ids[0]];
   if (v == 0)
-    DZ_LAUNCH_NAMED(tag, um::umma_gemm_kernel<32>, (unsigned)l.nctas, um::kThreadsU, smem, stream, lm, d_ctas + l.cta0, d_probs, d_ops, l.nmaps, l.stages,
+    DZ_LAUNCH_NAMED(tag, um::umma_gemm_kernel<32>, (unsigned)l.nctas, um::kThreadsG, smem, stream, lm, d_ctas + l.cta0, d_probs, d_ops, l.nmaps, stages,
                     l.stage_bytes, d_trace);
   else
-    DZ_LAUNCH_NAMED(tag, um::umma_gemm_kernel<64>, (unsigned)l.nctas, um::kThreadsU, smem, stream, lm, d_ctas + l.cta0, d_probs, d_ops, l.nmaps, l.stages,
+    DZ_LAUNCH_NAMED(tag, um::umma_gemm_kernel<64>, (unsigned)l.nctas, um::kThreadsG, smem, stream, lm, d_ctas + l.cta0, d_probs, d_ops, l.nmaps, stages,
                     l.stage_bytes, d_trace);
   return DZ_OK;
 }

@@ -93,16 +93,8 @@ using namespace tc;
 
 constexpr int kStagesMax = 8;
 constexpr int kConvWarps = 8;
-constexpr int kThreadsU = (2 + 4 + kConvWarps) * 32;   // producer, mma, 4 epilogue, 8 converter warps
-
-// One lane of a converged warp.  With elect.sync ptxas knows that exactly one thread runs the guarded region and
-// emits the tcgen05.mma / TMA instructions back to back; under `if (lane == 0)` it wraps EVERY such instruction in an
-// ELECT / BRA.U.ANY loop over the possibly-active lanes (measured: ~75 cycles per MMA instead of the pipe's 16-32).
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n .reg .pred P;\n elect.sync _|P, 0xffffffff;\n selp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
-  return pred != 0;
-}
+constexpr int kThreadsU = (2 + 4 + kConvWarps) * 32;   // producer, mma, 4 epilogue, 8 converter warps (conv1 kernels)
+constexpr int kThreadsG = kThreadsU + 32;              // umma_gemm_kernel: + a second MMA issuer (warp 14)
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -265,10 +257,15 @@ __device__ __forceinline__ float4* stage_chunk(uint8_t* base, int r, int c) {
 }
 
 // grid = number of CTA descriptors; dynamic smem = kCtlBytes + stages * stage_bytes + 1024 (alignment slack).
-// Warp roles: 0 TMA producer | 1 MMA issuer | 2-5 accumulator drain (TMEM lane quarters) | 6-13 operand converters.
+// Warp roles: 0 TMA producer | 1 and 14 MMA issuers | 2-5 accumulator drain (TMEM lane quarters) | 6-13 operand converters.
 // All twelve warps 2-13 take part in the final store phase (tile staged in shared memory, written out in full rows).
+// The two MMA warps alternate accumulation runs (warp 1: even runs into TMEM buffer 0, warp 14: odd runs into buffer 1):
+// the per-stage barrier waits / fences / commits of one overlap the MMAs of the other.
+// One k-step = TWO instructions: Ah x [Bh | Bl] (N = 2*NJT: hi and lo tiles of B are adjacent in shared memory, so one
+// descriptor spans both; columns [0,NJT) get Ah*Bh, [NJT,2*NJT) get Ah*Bl) and Al x Bh (N = NJT, added into [0,NJT)); the
+// drain adds the two column halves.  Against three N = NJT instructions this reads the A tile twice instead of 3 times.
 template <int NJT>
-__global__ void __launch_bounds__(kThreadsU, 1)
+__global__ void __launch_bounds__(kThreadsG, 1)
     umma_gemm_kernel(const __grid_constant__ UmMaps maps, const UmCta* __restrict__ ctas, const UmProblem* __restrict__ probs,
                      const UmTmaOp* __restrict__ ops, int nmaps, int stages, uint32_t stage_bytes, long long* __restrict__ trace) {
   if (threadIdx.x < nmaps) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.m[threadIdx.x])) : "memory");
@@ -296,18 +293,18 @@ __global__ void __launch_bounds__(kThreadsU, 1)
   static_assert(kCtlBytes % 1024 == 0, "stage base must stay 1024-byte aligned");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kTmemCols = 2 * NJT;
+  constexpr int kTmemCols = 4 * NJT;                       // two buffers x (Ah*Bh + Al*Bh | Ah*Bl)
 
   // The CTA's problem and its whole TMA program go to shared memory once (coalesced): the producer's per-stage
   // work is then a shared-memory read, not a dependent global load per stage.
   {
     const uint4* src = reinterpret_cast<const uint4*>(probs + cta.prob);
     uint4* dst = reinterpret_cast<uint4*>(p_smem);
-    for (int i = threadIdx.x; i < (int)(sizeof(UmProblem) / 16); i += kThreadsU) dst[i] = src[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(UmProblem) / 16); i += kThreadsG) dst[i] = src[i];
     const int nvec = min(nst * (int)cta.ops_per_stage, kMaxOpsPerCta) * 2;
     const uint4* osrc = reinterpret_cast<const uint4*>(ops + cta.op0);
     uint4* odst = reinterpret_cast<uint4*>(ops_smem);
-    for (int i = threadIdx.x; i < nvec; i += kThreadsU) odst[i] = osrc[i];
+    for (int i = threadIdx.x; i < nvec; i += kThreadsG) odst[i] = osrc[i];
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -334,91 +331,101 @@ __global__ void __launch_bounds__(kThreadsU, 1)
   // stores that stay row-per-lane coalesced (lane = D row, unit stride along i) are written straight from registers
   const bool direct = p.epi == UM_EPI_PARTIAL && p.sc_i == 1;
 
-  if (warp == 0) {
-    // ---------------------------------------------------------------- TMA producer: lane q issues op q of the stage
-    const int nops = (int)cta.ops_per_stage;
+  // TMA producers.  Issuing a tensor load costs the issuing warp ~130-300 cycles of operand set-up (shared-memory read of the
+  // op, address arithmetic, moves to uniform registers), far more than the TMA unit needs — so the ops of a stage are spread
+  // over warps: warp 0 always; when no operand needs conversion the eight converter warps have nothing else to do and
+  // each takes ops too (op q -> producer q % nprod).  Every producer waits for the slot itself; warp 0 posts the byte
+  // count (bytes may land before the expect_tx arrive: the phase cannot complete without that arrive).
+  const int nops = (int)cta.ops_per_stage;
+  const int nprod = any_conv ? 1 : min(nops, 1 + kConvWarps);
+  const int pidx = warp == 0 ? 0 : (warp >= 6 && warp < 14 ? warp - 5 : 99);
+  if (pidx < nprod) {
     int s = 0;
     uint32_t ph = 0;
     uint32_t st_addr = smem_u32(stage_base);
     int oi = 0;
     dz::pdl_enter();
-    if (tr && lane == 0) { trace[323] = clock64(); trace[324] = clock64(); }
+    if (tr && warp == 0 && lane == 0) { trace[323] = clock64(); trace[324] = clock64(); }
+    const int my_ops = (nops - pidx + nprod - 1) / nprod;      // ops pidx, pidx + nprod, ...
     for (int it = 0; it < nst; ++it) {
       mbar_wait(&empty[s], ph ^ 1u);
-      // lane q prepares and issues op q: the operand set-up (shared-memory read, address arithmetic, moves to uniform
-      // registers) runs SIMD across the lanes and only the UTMALDG instructions themselves are serialised
-      // (measured: ~125 cycles per op; one elected thread issuing all ops in a loop: ~300 cycles per op)
-      if (lane == 0) mbar_expect_tx(&full[s], cta.tx_bytes);
+      if (pidx == 0 && lane == 0) mbar_expect_tx(&full[s], cta.tx_bytes);
       __syncwarp();
-      if (lane < nops) {
-        const int o = oi + lane;
+      if (lane < my_ops) {   // lanes prepare their ops SIMD; only the UTMALDG instructions themselves are serialised
+        const int o = oi + pidx + lane * nprod;
         const UmTmaOp op = o < kMaxOpsPerCta ? ops_smem[o] : ops[cta.op0 + o];   // long programs spill to the global table
         tma_load_5d(st_addr + op.smem_off, &maps.m[op.map], &full[s], op.c[0], op.c[1], op.c[2], op.c[3], op.c[4]);
       }
-      if (tr && lane == 0 && it < 64) trace[it] = clock64();                                       // [0,64): TMA issued
+      if (tr && warp == 0 && lane == 0 && it < 64) trace[it] = clock64();                          // [0,64): TMA issued
       __syncwarp();
       oi += nops;
       ++s; st_addr += stage_bytes;
       if (s == ST) { s = 0; ph ^= 1u; st_addr = smem_u32(stage_base); }
     }
-  } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
+  }
+  if (warp == 0) {
+  } else if (warp == 1 || warp == 14) {
+    // ---------------------------------------------------------------- MMA issuers (runs of parity `mw`, TMEM buffer `mw`)
     // Descriptors: the upper word (SBO, version, layout type) and the LBO field are loop invariants; the start-address
     // field (bits 0-13, address >> 4 — shared memory is < 256 KB, so sums never carry out of the field) is advanced
     // with plain adds.
-    const uint32_t idesc = make_idesc(128, NJT, (int)p.A.mn_major, (int)p.B.mn_major);
+    const int mw = warp == 1 ? 0 : 1;
+    const uint32_t idesc2 = make_idesc(128, 2 * NJT, (int)p.A.mn_major, (int)p.B.mn_major);
+    const uint32_t idesc1 = make_idesc(128, NJT, (int)p.A.mn_major, (int)p.B.mn_major);
     const uint32_t a_up = (p.A.mn_major ? (512u >> 4) : (1024u >> 4)) | (1u << 14) | ((p.A.mn_major ? 1u : 2u) << 29);
     const uint32_t b_up = (p.B.mn_major ? (512u >> 4) : (1024u >> 4)) | (1u << 14) | ((p.B.mn_major ? 1u : 2u) << 29);
     const uint32_t a_lbo = (((p.A.mn_major ? p.A.lbo : 16u) >> 4) & 0x3FFFu) << 16;
     const uint32_t b_lbo = (((p.B.mn_major ? p.B.lbo : 16u) >> 4) & 0x3FFFu) << 16;
     const uint32_t a_stepq = p.A.kstep >> 4, b_stepq = p.B.kstep >> 4;
-    const uint32_t a_pbq = p.A.part_bytes >> 4, b_pbq = p.B.part_bytes >> 4;
-    const bool a_exact = p.A.nparts == 1, b_exact = p.B.nparts == 1;
+    const uint32_t a_pbq = p.A.part_bytes >> 4;
     const int ksteps = (int)p.ksteps;
     const uint32_t stq0 = smem_u32(stage_base) >> 4, stageq = stage_bytes >> 4, a_bytesq = a_bytes >> 4;
-    int s = 0, in_run = 0, run = 0;
-    uint32_t ph = 0, stq = stq0;
-    for (int it = 0; it < nst; ++it) {
+    // Slot ownership must be static for the two-warp scheme (a warp may only revisit slots it consumed itself, otherwise
+    // the 1-bit phase of full[s] could alias when it runs ahead of the other warp): ST a multiple of 2 * run_stages
+    // (UmPlan::launch rounds the stage count down accordingly).  Otherwise warp 1 issues every run and warp 14 idles.
+    const int nw = (ST % (2 * run_stages) == 0) ? 2 : 1;
+    for (int run = mw; run < nruns && mw < nw; run += nw) {
       const int buf = run & 1;
-      if (in_run == 0) {
-        mbar_wait(&acc_empty[buf], (((uint32_t)run >> 1) & 1u) ^ 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      }
-      mbar_wait(any_conv ? &ready[s] : &full[s], ph);
+      const uint32_t d = tmem_base + (uint32_t)(buf * 2 * NJT);
+      mbar_wait(&acc_empty[buf], (((uint32_t)run >> 1) & 1u) ^ 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const bool last_of_run = in_run == run_stages - 1 || it == nst - 1;
-      if (elect_one()) {
-        if (tr && it < 64) trace[64 + it] = clock64();                                             // [64,128): stage data ready
-        uint32_t ah = a_lbo + stq, al = ah + a_pbq;
-        uint32_t bh = b_lbo + stq + a_bytesq, bl = bh + b_pbq;
-        const uint32_t d = tmem_base + (uint32_t)(buf * NJT);
-        uint32_t acc = in_run > 0 ? 1u : 0u;
-        auto kstep = [&]() {
-          const uint64_t dah = ((uint64_t)a_up << 32) | ah, dal = ((uint64_t)a_up << 32) | al;
-          const uint64_t dbh = ((uint64_t)b_up << 32) | bh, dbl = ((uint64_t)b_up << 32) | bl;
-          if (!a_exact) { mma_tf32(d, dal, dbh, idesc, acc); acc = 1u; }   // small cross terms first
-          if (!b_exact) { mma_tf32(d, dah, dbl, idesc, acc); acc = 1u; }
-          mma_tf32(d, dah, dbh, idesc, acc);
-          acc = 1u;
-          ah += a_stepq; al += a_stepq; bh += b_stepq; bl += b_stepq;
-        };
-        if (ksteps == 4) {
+      int it = run * run_stages;
+      const int run_end = min(it + run_stages, nst);
+      int s = it % ST;
+      uint32_t ph = (uint32_t)(it / ST) & 1u;
+      for (int in_run = 0; it < run_end; ++it, ++in_run) {
+        mbar_wait(any_conv ? &ready[s] : &full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          if (tr && it < 64) trace[64 + it] = clock64();                                           // [64,128): stage data ready
+          const uint32_t stq = stq0 + (uint32_t)s * stageq;
+          uint32_t ah = a_lbo + stq, al = ah + a_pbq;
+          uint32_t bh = b_lbo + stq + a_bytesq;
+          uint32_t acc = in_run > 0 ? 1u : 0u;
+          auto kstep = [&]() {
+            const uint64_t dah = ((uint64_t)a_up << 32) | ah, dal = ((uint64_t)a_up << 32) | al;
+            const uint64_t dbh = ((uint64_t)b_up << 32) | bh;
+            mma_tf32(d, dah, dbh, idesc2, acc);             // [Ah*Bh | Ah*Bl]
+            mma_tf32(d, dal, dbh, idesc1, 1u);              // += Al*Bh
+            acc = 1u;
+            ah += a_stepq; al += a_stepq; bh += b_stepq;
+          };
+          if (ksteps == 4) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) kstep();
-        } else {
-          for (int k = 0; k < ksteps; ++k) kstep();
+            for (int k = 0; k < 4; ++k) kstep();
+          } else {
+            for (int k = 0; k < ksteps; ++k) kstep();
+          }
+          mma_commit(&empty[s]);
+          if (it == run_end - 1) mma_commit(&acc_full[buf]);
+          if (it == nst - 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel's set-up overlaps our epilogue
+          if (tr && it < 64) trace[128 + it] = clock64();                                          // [128,192): MMAs issued
         }
-        mma_commit(&empty[s]);
-        if (last_of_run) mma_commit(&acc_full[buf]);
-        if (it == nst - 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next kernel's set-up overlaps our epilogue
-        if (tr && it < 64) trace[128 + it] = clock64();                                            // [128,192): MMAs issued
+        __syncwarp();
+        if (++s == ST) { s = 0; ph ^= 1u; }
       }
-      __syncwarp();
-      ++s; stq += stageq;
-      if (s == ST) { s = 0; ph ^= 1u; stq = stq0; }
-      if (last_of_run) { in_run = 0; ++run; } else { ++in_run; }
     }
-    if (nst == 0 && elect_one()) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (nst == 0 && mw == 0 && elect_one()) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   } else if (warp < 6) {
     // ---------------------------------------------------------------- accumulator drain
     const int quarter = warp & 3;
@@ -441,14 +448,14 @@ __global__ void __launch_bounds__(kThreadsU, 1)
       mbar_wait(&acc_full[buf], ((uint32_t)run >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (tr && warp == 2 && lane == 0 && run < 64) trace[192 + run] = clock64();                  // [192,256): accumulator ready
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * NJT);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 2 * NJT);
 #pragma unroll
-      for (int c0 = 0; c0 < NJT; c0 += 32) {
+      for (int c0 = 0; c0 < 2 * NJT; c0 += 32) {            // columns [0,NJT): Ah*Bh + Al*Bh, [NJT,2*NJT): Ah*Bl
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c0, r);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int t = 0; t < 32; ++t) sum[c0 + t] += __uint_as_float(r[t]);
+        for (int t = 0; t < 32; ++t) sum[(c0 % NJT) + t] += __uint_as_float(r[t]);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -498,9 +505,9 @@ __global__ void __launch_bounds__(kThreadsU, 1)
       if (s == ST) { s = 0; ph ^= 1u; st = stage_base; }
     }
   }
-  if (!direct && warp >= 2) {
+  if (!direct && warp >= 2 && warp < 14) {
     // ---------------------------------------------------------------- cooperative store phase (warps 2-13, 384 threads)
-    if (warp >= 6 && !any_conv) dz::pdl_enter();
+    if (warp >= 6 && !any_conv) dz::pdl_enter();          // idle converter warps: first access to global data is here
     bar_sync_coop();
     const int tid = threadIdx.x - 64;
     const int NJ = p.NJ, cpr = NJ >> 2;

@@ -638,18 +638,19 @@ __global__ void __launch_bounds__(256) um_fcd_finish_kernel(const float* __restr
 // Partial sums: a block owns 32 consecutive float4 columns; its 8 thread groups stride over the S partials (so the
 // up-to-148 loads of one column are 8 independent chains instead of one dependent chain), then group sums are added in
 // group order through shared memory — a fixed association, hence bit-deterministic.
-constexpr int kWgSumBlocks = 288, kWgChunkRows = 128, kWgMaxChunks = 256, kWgGroups = 8;
-struct WgFinish { const float* partial; int S; long long stride; int KN; float* dW; const float* G; int M, N; float* db; float* scratch; unsigned int* ticket; };
-struct WgFinishBatch { WgFinish f[4]; int n; };
+constexpr int kWgChunkRows = 128, kWgMaxChunks = 256, kWgGroups = 8;
+// norm_part: this layer's slots of the split global gradient norm: [0, sum_blocks) = sum of squares of the dW values each
+// sum block wrote, [sum_blocks] = sum of squares of db (dz_learner.cu: split_norm).
+struct WgFinish { const float* partial; int S; long long stride; int KN; float* dW; const float* G; int M, N; float* db; float* scratch;
+                  unsigned int* ticket; int sum_blocks; float* norm_part; };
 
-__global__ void __launch_bounds__(256) um_wgrad_finish_kernel(const __grid_constant__ WgFinishBatch b) {
+__global__ void __launch_bounds__(256) um_wgrad_finish_kernel(const __grid_constant__ WgFinish f) {
   dz::pdl_enter();
-  const WgFinish& f = b.f[blockIdx.y];
   __shared__ float4 red4[256];
   __shared__ bool last;
-  if (blockIdx.x >= kWgSumBlocks) {
+  if ((int)blockIdx.x >= f.sum_blocks) {
     float* red = reinterpret_cast<float*>(red4);
-    const int chunk = blockIdx.x - kWgSumBlocks, nchunks = (f.M + kWgChunkRows - 1) / kWgChunkRows;
+    const int chunk = blockIdx.x - f.sum_blocks, nchunks = (f.M + kWgChunkRows - 1) / kWgChunkRows;
     if (!f.db || chunk >= nchunks) return;
     const int n = threadIdx.x % f.N, g = threadIdx.x / f.N, G = 256 / f.N;
     const int m1 = min(f.M, (chunk + 1) * kWgChunkRows);
@@ -674,18 +675,27 @@ __global__ void __launch_bounds__(256) um_wgrad_finish_kernel(const __grid_const
       for (int c = g; c < nchunks; c += G) t += __ldcg(f.scratch + c * 64 + n);
       red[threadIdx.x] = t;
       __syncthreads();
+      float sq = 0.f;
       if (threadIdx.x < f.N) {
         float tt = 0.f;
         for (int q = 0; q < G; ++q) tt += red[q * f.N + threadIdx.x];
         f.db[threadIdx.x] = tt;
+        sq = tt * tt;
       }
-      if (threadIdx.x == 0) *f.ticket = 0;
+      __syncthreads();
+      red[threadIdx.x] = sq;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int q = 0; q < f.N; ++q) tot += red[q];
+        if (f.norm_part) f.norm_part[f.sum_blocks] = tot;
+        *f.ticket = 0;
+      }
     }
     return;
   }
   const int total4 = f.KN >> 2;
   const int col = blockIdx.x * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;
-  if (blockIdx.x * 32 >= total4) return;
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (col < total4) {
     const float* src = f.partial + ((long long)col << 2);
@@ -697,13 +707,19 @@ __global__ void __launch_bounds__(256) um_wgrad_finish_kernel(const __grid_const
   }
   red4[threadIdx.x] = v;
   __syncthreads();
-  if (g == 0 && col < total4) {
+  if (g == 0) {
+    float sq = 0.f;
+    if (col < total4) {
 #pragma unroll
-    for (int q = 1; q < kWgGroups; ++q) {
-      const float4 x = red4[q * 32 + threadIdx.x];
-      v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+      for (int q = 1; q < kWgGroups; ++q) {
+        const float4 x = red4[q * 32 + threadIdx.x];
+        v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+      }
+      *reinterpret_cast<float4*>(f.dW + ((long long)col << 2)) = v;
+      sq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
     }
-    *reinterpret_cast<float4*>(f.dW + ((long long)col << 2)) = v;
+    sq = warp_sum(sq);
+    if (threadIdx.x == 0 && f.norm_part) f.norm_part[blockIdx.x] = sq;
   }
 }
 
@@ -1501,26 +1517,27 @@ int um_wgrad_conv3(UmNet* n, void* stream) { return n->plan.launch("conv3_wgrad"
 int um_wgrad_conv2(UmNet* n, void* stream) { return n->plan.launch("conv2_wgrad", n->l_wconv2, stream, n->tr("conv2_wgrad")); }
 
 // dW / db of conv3 and conv2 from the split partials (+ optionally conv1's FMA partials in the same launch).
-int um_wgrad_finish(UmNet* n, float* dW3, float* db3, float* dW2, float* db2, const float* c1_partial, int c1_splits, float* dW1,
-                    float* db1, void* stream) {
-  WgFinishBatch b;
-  memset(&b, 0, sizeof(b));
+namespace {
+int wg_sum_blocks(int layer) { const int KN[3] = {256 * 32, 512 * 64, 576 * 64}; return (KN[layer - 1] / 4 + 31) / 32; }
+int wg_slot_base(int layer) { int b = 0; for (int L = 3; L > layer; --L) b += wg_sum_blocks(L) + 1; return b; }
+}  // namespace
+
+int um_norm_slots(UmNet*) { return wg_slot_base(1) + wg_sum_blocks(1) + 1; }
+
+// dW / db of one conv layer (1..3) from its split partials; norm_parts (optional): base of the split-norm slot array.
+int um_wgrad_finish_layer(UmNet* n, int layer, float* dW, float* db, float* norm_parts, void* stream) {
   float* sc = n->wg_scratch;
-  b.f[0] = WgFinish{n->wg3_part, n->wg3_splits, 576 * 64, 576 * 64, dW3, n->dact_f32[2], n->d.B * n->h3 * n->w3, 64, db3, sc, n->wg_ticket};
-  b.f[1] = WgFinish{n->wg2_part, n->wg2_splits, 512 * 64, 512 * 64, dW2, n->dact_f32[1], n->d.B * n->h2 * n->w2, 64, db2, sc + 256 * 64, n->wg_ticket + 1};
-  b.n = 2;
-  if (c1_partial) {   // conv1 partials of the FMA kernel: [splits][256 + 1 (bias row)][32]; the bias is recomputed here from dact1
-    b.f[2] = WgFinish{c1_partial, c1_splits, 257 * 32, 256 * 32, dW1, n->dact_f32[0], n->d.B * n->h1 * n->w1, 32, db1, sc + 2 * 256 * 64, n->wg_ticket + 2};
-    b.n = 3;
-  } else if (dW1) {   // conv1 partials of conv1_wgrad_umma_kernel: one [256][32] per CTA
-    b.f[2] = WgFinish{n->wg1_part, n->wg1_ctas, 256 * 32, 256 * 32, dW1, n->dact_f32[0], n->d.B * n->h1 * n->w1, 32, db1, sc + 2 * 256 * 64, n->wg_ticket + 2};
-    b.n = 3;
-  }
-  int max_chunks = 1;
-  for (int q = 0; q < b.n; ++q) max_chunks = std::max(max_chunks, (b.f[q].M + kWgChunkRows - 1) / kWgChunkRows);
-  if (max_chunks > kWgMaxChunks) return fail(DZ_EINVAL, "bias-gradient reduction: too many row chunks");
-  dim3 grid((unsigned)(kWgSumBlocks + max_chunks), (unsigned)b.n);
-  DZ_LAUNCH_NAMED("wgrad_finish", um_wgrad_finish_kernel, grid, 256, 0, stream, b);
+  WgFinish f;
+  memset(&f, 0, sizeof(f));
+  if (layer == 3) f = WgFinish{n->wg3_part, n->wg3_splits, 576 * 64, 576 * 64, dW, n->dact_f32[2], n->d.B * n->h3 * n->w3, 64, db, sc, n->wg_ticket, 0, nullptr};
+  else if (layer == 2) f = WgFinish{n->wg2_part, n->wg2_splits, 512 * 64, 512 * 64, dW, n->dact_f32[1], n->d.B * n->h2 * n->w2, 64, db, sc + 256 * 64, n->wg_ticket + 1, 0, nullptr};
+  else f = WgFinish{n->wg1_part, n->wg1_ctas, 256 * 32, 256 * 32, dW, n->dact_f32[0], n->d.B * n->h1 * n->w1, 32, db, sc + 2 * 256 * 64, n->wg_ticket + 2, 0, nullptr};
+  f.sum_blocks = wg_sum_blocks(layer);
+  f.norm_part = norm_parts ? norm_parts + wg_slot_base(layer) : nullptr;
+  const int chunks = (f.M + kWgChunkRows - 1) / kWgChunkRows;
+  if (chunks > kWgMaxChunks) return fail(DZ_EINVAL, "bias-gradient reduction: too many row chunks");
+  const char* tags[3] = {"wgrad_finish1", "wgrad_finish2", "wgrad_finish3"};
+  DZ_LAUNCH_NAMED(tags[layer - 1], um_wgrad_finish_kernel, (unsigned)(f.sum_blocks + chunks), 256, 0, stream, f);
   return DZ_OK;
 }
 

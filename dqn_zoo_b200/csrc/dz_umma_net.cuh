@@ -49,8 +49,9 @@ int um_split_dact3(UmNet* n, void* stream);                                    /
 int um_wgrad_conv1(UmNet* n, const uint8_t* const* rows0, void* stream);       // uint8 rows x dact1 -> one partial per CTA
 int um_wgrad_conv3(UmNet* n, void* stream);                                    // act2 x dact3 -> split partials
 int um_wgrad_conv2(UmNet* n, void* stream);                                    // act1 x dact2 -> split partials
-int um_wgrad_finish(UmNet* n, float* dW3, float* db3, float* dW2, float* db2, const float* c1_partial, int c1_splits, float* dW1,
-                    float* db1, void* stream);                                 // partial sums + bias gradients, one launch
+int um_wgrad_finish_layer(UmNet* n, int layer, float* dW, float* db, float* norm_parts, void* stream);   // partial sums + bias gradient of
+                                                                               // conv layer 1..3 (+ its split-norm partials)
+int um_norm_slots(UmNet* n);                                                   // floats of the split-norm slot array
 int um_backward_conv3(UmNet* n, void* stream);                                 // dact3 -> dact2
 int um_backward_conv2(UmNet* n, void* stream);                                 // dact2 -> dact1
 

@@ -16,10 +16,11 @@ import bench  # noqa: E402
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--agent', default='rainbow')
+  ap.add_argument('--graph', action='store_true', help='stamp inside CUDA-graph replays (steady-state cache / DRAM conditions)')
   ap.add_argument('--tags', default='conv2_fwd,conv3_fwd,fc1_fwd,fc1_dgrad,conv3_dgrad,conv2_dgrad,conv3_wgrad,conv2_wgrad')
   a = ap.parse_args()
   from dqn_zoo_b200 import _lib
-  args = argparse.Namespace(agent=a.agent, capacity=131072, batch=32, seed=1, no_graph=True)
+  args = argparse.Namespace(agent=a.agent, capacity=131072, batch=32, seed=1, no_graph=not a.graph)
   torch.cuda.set_device(0)
   ag, rep = bench.build_agent(args, 0, torch.device('cuda', 0))
   for _ in range(5):
@@ -28,7 +29,12 @@ def main():
   for tag in a.tags.split(','):
     tr = torch.zeros(512, dtype=torch.int64, device='cuda')
     _lib.call('dz_test_learner_trace', ag.learner._h, tag.encode(), tr.data_ptr())
-    ag.learn()
+    if a.graph:
+      ag._graph = None          # recapture with the trace pointer baked into the launch
+      for _ in range(8):
+        ag.learn()
+    else:
+      ag.learn()
     torch.cuda.synchronize()
     _lib.call('dz_test_learner_trace', ag.learner._h, b'', 0)
     t = tr.cpu().numpy()
