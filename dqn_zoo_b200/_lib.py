@@ -105,6 +105,7 @@ _SIGNATURES = {
     'dz_learner_generate_randomness': (i32, [vp, u64, vp, vp, vp]),
     'dz_learner_generate_randomness_async': (i32, [vp, u64, vp, vp, vp]),
     'dz_learner_q_values': (i32, [vp, vp, vp, vp, vp, vp]),
+    'dz_learner_act_batch': (i32, [vp, vp, i32, vp, vp, vp, f32, vp, vp, vp]),
     'dz_learner_sync_target': (i32, [vp, vp]),
     'dz_test_u8_to_unit': (i32, [vp, vp]),
     'dz_test_tc_set_variant': (i32, [i32]),

@@ -530,3 +530,54 @@ class EpsilonGreedyActor(parts.Agent):
 
 AGENTS = {'dqn': Dqn, 'double_q': DoubleQ, 'prioritized': PrioritizedDqn, 'c51': C51, 'qrdqn': QrDqn,
           'rainbow': Rainbow, 'iqn': Iqn}
+
+
+class BatchedEpsilonGreedyActor:
+  """E independent actor streams served by ONE network evaluation per tick (the many-actors shape of
+  parts.py:342-411 with dqn/agent.py:121-131 acting): observations of all streams -> `Learner.act_batch` (online forward,
+  q-values and the epsilon-greedy choice on the device) -> one device-to-host copy of E actions.
+
+  `learner` is the training agent's `Learner` (shared parameters, as the reference's actors read the learner's online
+  params) or any `Learner` whose batch size is >= E.  Exploration uniforms come from a host RandomState seeded from
+  `rng_key` (2E floats per tick; the reference draws with the JAX PRNG per actor).  Rainbow: one noise sample per tick is
+  shared by the E streams; IQN: every stream gets its own tau samples."""
+
+  def __init__(self, learner: learner_lib.Learner, num_streams: int, exploration_epsilon, rng_key):
+    if num_streams < 1 or num_streams > learner.batch_size:
+      raise ValueError('num_streams must be in [1, learner.batch_size]')
+    self._learner = learner
+    self._E = int(num_streams)
+    self._epsilon = exploration_epsilon
+    seed = int(np.asarray(rng_key).reshape(-1)[-1]) & 0x7FFFFFFF
+    self._rng = np.random.RandomState(seed)
+    self._seed = seed
+    self._t = 0
+    self._explore_host = torch.zeros((2, self._E), dtype=torch.float32).pin_memory()
+    self._explore_dev = torch.zeros((2, self._E), dtype=torch.float32, device=learner.device)
+    self._actions_host = torch.zeros(self._E, dtype=torch.int32).pin_memory()
+    self.q_values = None
+
+  def step(self, observations) -> np.ndarray:
+    """observations: [E, H, W, C] uint8 (device tensor, e.g. the stacks of processors.BatchedAtariPreprocessor, or host
+    array).  Returns the E actions as a host int32 array."""
+    L = self._learner
+    eps = self._epsilon(self._t) if callable(self._epsilon) else float(self._epsilon)
+    explore = None
+    if eps > 0.0:
+      self._explore_host.copy_(torch.from_numpy(self._rng.uniform(size=(2, self._E)).astype(np.float32)))
+      self._explore_dev.copy_(self._explore_host, non_blocking=True)
+      explore = self._explore_dev
+    taus = noise = None
+    kind = L.net.kind
+    if kind in ('iqn', 'rainbow'):
+      L.generate_randomness(self._seed)
+      if kind == 'iqn':
+        taus = L.taus[:self._E * L.net.tau_samples_policy] if hasattr(L.net, 'tau_samples_policy') else L.taus
+      else:
+        noise = L.noise
+    actions, self.q_values = L.act_batch(observations, epsilon=eps, explore=explore, taus=taus, noise=noise)
+    self._actions_host.copy_(actions, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    self._t += 1
+    return self._actions_host.numpy().copy()
+

@@ -776,6 +776,7 @@ __global__ void loss_mean_kernel(const float* __restrict__ terms, int B, float* 
 }
 
 // q_values of one head pass (select_action): c51/rainbow expectation, qr/iqn mean, dqn identity.
+// blockIdx.x = environment stream (batched acting); one block for the single-observation call.
 __global__ void __launch_bounds__(128) q_values_kernel(int kind, int A, int atoms, int nq, float vmax, const float* out,
                                                        const float* adv, const float* val, float* q) {
   dz::pdl_enter();
@@ -783,6 +784,12 @@ __global__ void __launch_bounds__(128) q_values_kernel(int kind, int A, int atom
   float* red = sm;
   float* logit = sm + 32;
   const int tid = threadIdx.x;
+  {
+    const long long e = blockIdx.x;
+    const long long per_img = (kind == DZ_C51 || kind == DZ_RAINBOW) ? (long long)A * atoms
+                              : ((kind == DZ_QRDQN || kind == DZ_IQN) ? (long long)nq * A : (long long)A);
+    out += e * per_img; adv += e * per_img; if (val) val += e * atoms; q += e * A;
+  }
   for (int a = 0; a < A; ++a) {
     float res;
     if (kind == DZ_C51 || kind == DZ_RAINBOW) {
@@ -981,6 +988,22 @@ __global__ void __launch_bounds__(256) optimizer_kernel(OptArgs o) {
   }
 }
 
+// epsilon-greedy over q[E][A] (dqn/agent.py:121-127): first maximum wins, as np.argmax / jnp.argmax.
+__global__ void act_select_kernel(const float* __restrict__ q, int A, int E, const float* __restrict__ explore, float eps,
+                                  int32_t* __restrict__ actions) {
+  dz::pdl_enter();
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  int best = 0;
+  float bq = q[(long long)e * A];
+  for (int a = 1; a < A; ++a) {
+    const float v = q[(long long)e * A + a];
+    if (v > bq) { bq = v; best = a; }
+  }
+  if (explore != nullptr && explore[e] < eps) best = min((int)(explore[E + e] * (float)A), A - 1);
+  actions[e] = best;
+}
+
 __global__ void make_row_table_kernel(const uint8_t* base, long long stride, int n, const uint8_t** table) {
   dz::pdl_enter();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1163,7 +1186,7 @@ int64_t carve(dz_learner* l, char* base) {
   l->ticket = w.take<unsigned int>(4);
   l->rows_sample[0] = w.take<const uint8_t*>(B);
   l->rows_sample[1] = w.take<const uint8_t*>(B);
-  l->rows_act = w.take<const uint8_t*>(4);
+  l->rows_act = w.take<const uint8_t*>(B > 4 ? B : 4);
   l->s_a = w.take<int32_t>(B);
   l->s_r = w.take<float>(B);
   l->s_d = w.take<float>(B);
@@ -2537,6 +2560,43 @@ int dz_learner_q_values(dz_learner* l, const uint8_t* d_obs, const float* d_taus
   }
   size_t smem = (32 + c.num_atoms + 8) * sizeof(float);
   DZ_LAUNCH(q_values_kernel, 1, 128, smem, stream, c.kind, c.num_actions, c.num_atoms, nq, c.vmax, l->out[1], l->out[1], l->outv[1], d_q_out);
+  return DZ_OK;
+}
+
+// Batched acting (parts.py:342-411 with many actors; dqn/agent.py:121-131,169-177): online forward on E <= batch observations
+// in one enqueue, q-values [E][A], and the epsilon-greedy choice on the device — one D2H of E actions per tick instead of a
+// D2H sync per decision.  d_obs: E contiguous observations (H*W*C bytes each).  d_explore: [2][E] uniforms in [0,1) or
+// NULL (greedy): action = u0 < epsilon ? floor(u1 * A) : argmax (first maximum, as np.argmax).  IQN: d_taus is
+// [E][tau_samples_policy]; rainbow: ONE noise apply shared by the E streams of the tick (the reference's actors each draw
+// their own: statistically the same exploration, not the same sample path).
+int dz_learner_act_batch(dz_learner* l, const uint8_t* d_obs, int32_t E, const float* d_taus, const float* d_noise,
+                         const float* d_explore, float epsilon, float* d_q_out, int32_t* d_actions, void* stream) {
+  const dz_learner_config& c = l->cfg;
+  const float* on = l->buf.d_online;
+  if (E < 1 || E > l->B) return fail(DZ_EINVAL, "act_batch: 1 <= E <= learner batch");
+  if (!d_obs || !d_q_out || !d_actions) return fail(DZ_EINVAL, "act_batch: null buffer");
+  DZ_TRY(join_side(l, stream));
+  const long long obs_bytes = (long long)l->d.H * l->d.W * l->d.C;
+  DZ_LAUNCH(make_row_table_kernel, (unsigned)ceil_div(E, 64), 64, 0, stream, d_obs, obs_bytes, (int)E, l->rows_act);
+  TorsoJob job{on, l->rows_act, 1};
+  DZ_TRY(forward_torso(l, &job, 1, E, stream));
+  Pass pass{on, nullptr, 1, 1, 0};
+  int nq = 1;
+  if (c.kind == DZ_IQN) {
+    if (!d_taus) return fail(DZ_EINVAL, "iqn act_batch needs taus[E][tau_samples_policy]");
+    const float* taus[1] = {d_taus};
+    DZ_TRY(forward_heads_iqn(l, &pass, 1, E, taus, false, stream));
+    nq = c.tau_samples_policy;
+  } else if (c.kind == DZ_RAINBOW) {
+    if (!d_noise) return fail(DZ_EINVAL, "rainbow act_batch needs one apply of noise");
+    DZ_TRY(forward_heads_rainbow(l, &pass, 1, E, d_noise, stream));
+  } else {
+    DZ_TRY(forward_heads_plain(l, &pass, 1, E, stream));
+    nq = c.num_quantiles;
+  }
+  size_t smem = (32 + c.num_atoms + 8) * sizeof(float);
+  DZ_LAUNCH(q_values_kernel, (unsigned)E, 128, smem, stream, c.kind, c.num_actions, c.num_atoms, nq, c.vmax, l->out[1], l->out[1], l->outv[1], d_q_out);
+  DZ_LAUNCH(act_select_kernel, (unsigned)ceil_div(E, 128), 128, 0, stream, (const float*)d_q_out, c.num_actions, (int)E, d_explore, epsilon, d_actions);
   return DZ_OK;
 }
 

@@ -287,6 +287,24 @@ class Learner:
     self._keep_q = (obs, t, n)
     return self.q_out[:self.net.num_actions]
 
+  def act_batch(self, obs_u8: torch.Tensor, epsilon: float = 0.0, explore=None, taus=None, noise=None):
+    """Batched select_action for E <= batch_size environment streams in ONE enqueue: `obs_u8` is [E, H, W, C] uint8 (device
+    or host), `explore` a float32 [2, E] tensor of uniforms in [0, 1) (None: greedy).  Returns (actions int32 [E],
+    q_values float32 [E, num_actions]) as device tensors — the caller does one D2H of the actions per tick."""
+    obs = torch.as_tensor(obs_u8, device=self.device).contiguous()
+    E = int(obs.shape[0])
+    if not hasattr(self, '_act_q') or self._act_q.shape[0] < E:
+      self._act_q = torch.zeros((self.batch_size, self.net.num_actions), dtype=torch.float32, device=self.device)
+      self._act_a = torch.zeros(self.batch_size, dtype=torch.int32, device=self.device)
+    t = None if taus is None else torch.as_tensor(taus, device=self.device).to(torch.float32).contiguous()
+    n = None if noise is None else torch.as_tensor(noise, device=self.device).to(torch.float32).contiguous()
+    x = None if explore is None else torch.as_tensor(explore, device=self.device).to(torch.float32).contiguous()
+    _lib.call('dz_learner_act_batch', self._h, obs.data_ptr(), E, 0 if t is None else t.data_ptr(),
+              0 if n is None else n.data_ptr(), 0 if x is None else x.data_ptr(), float(epsilon), self._act_q.data_ptr(),
+              self._act_a.data_ptr(), _cstream())
+    self._keep_act = (obs, t, n, x)
+    return self._act_a[:E], self._act_q[:E]
+
   # -- fused sample -> update -> priority write-back -------------------------------------------------
   def make_learn_io(self, stage: torch.Tensor, prioritized: bool, priority_exponent: float):
     """Binds the per-step staging buffer (float64 view: [pos(int64) B | u_tree B | u_mix B | scalars 4])

@@ -287,6 +287,16 @@ int dz_learner_generate_randomness_async(dz_learner* l, uint64_t seed, float* d_
 int dz_learner_q_values(dz_learner* l, const uint8_t* d_obs, const float* d_taus, const float* d_noise,
                         float* d_q_out, void* stream);
 
+/* Batched acting for E <= batch independent environment streams (parts.py:342-411 run over many actors;
+ * dqn/agent.py:121-131,169-177): online forward on E observations in one enqueue, q-values [E][num_actions] and the
+ * epsilon-greedy choice on the device, so a tick costs ONE device-to-host copy of E int32 actions.
+ *   d_obs      E contiguous uint8 observations (obs_h*obs_w*obs_c bytes each), device memory
+ *   d_taus     iqn: [E][tau_samples_policy];  d_noise  rainbow: one noise apply, shared by the E streams of the tick
+ *   d_explore  [2][E] float32 uniforms in [0,1) (device) or NULL for greedy acting:
+ *              action = u0[e] < epsilon ? min(floor(u1[e] * num_actions), num_actions - 1) : first argmax of q[e] */
+int dz_learner_act_batch(dz_learner* l, const uint8_t* d_obs, int32_t E, const float* d_taus, const float* d_noise,
+                         const float* d_explore, float epsilon, float* d_q_out, int32_t* d_actions, void* stream);
+
 /* target <- online (dqn/agent.py:155-156): device-to-device copy of the blob. */
 int dz_learner_sync_target(dz_learner* l, void* stream);
 

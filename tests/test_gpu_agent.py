@@ -282,3 +282,52 @@ def test_train_eval_iteration_with_trackers_actor_and_checkpoint(kind, tmp_path)
     np.testing.assert_array_equal(a['online_params'][name], b['online_params'][name])
   rows = open(str(tmp_path / ('results_%s.csv' % kind))).read().strip().splitlines()
   assert rows[0].startswith('iteration,train_episode_return') and len(rows) == 4   # header + it0 + it1 + it1 again
+
+
+@pytest.mark.parametrize('kind', ['dqn', 'double_q', 'c51', 'qrdqn', 'iqn', 'rainbow'])
+def test_batched_acting_equals_per_stream_acting(kind):
+  """dz_learner_act_batch (E environment streams in one enqueue, epsilon-greedy on the device) against E calls of the
+  single-observation q_values path (dqn/agent.py:121-131): same q-values, first-argmax actions, and the documented
+  exploration rule action = u0 < eps ? floor(u1 * A) : argmax."""
+  from dqn_zoo_b200 import learner as dl
+  rs = np.random.RandomState(5)
+  E, A = 7, 6
+  L = dl.Learner(dl.NetworkSpec(kind, A), batch_size=8)
+  from oracle import learner_oracle as lo
+  L.set_params(lo.init_params(lo.NetSpec(kind, A), 3), also_target=True)
+  obs = torch.as_tensor(rs.randint(0, 256, size=(E, 84, 84, 4)).astype(np.uint8), device='cuda')
+  taus = noise = None
+  if kind == 'iqn':
+    taus = torch.as_tensor(rs.uniform(size=(E, 64)).astype(np.float32), device='cuda')
+  if kind == 'rainbow':
+    L.generate_randomness(11)
+    torch.cuda.synchronize()
+    noise = L.noise.clone()
+  explore = torch.as_tensor(rs.uniform(size=(2, E)).astype(np.float32), device='cuda')
+  eps = 0.4
+  actions, q = L.act_batch(obs, epsilon=eps, explore=explore, taus=taus, noise=noise)
+  torch.cuda.synchronize()
+  actions, q = actions.cpu().numpy(), q.cpu().numpy()
+  u = explore.cpu().numpy()
+  for e in range(E):
+    q1 = L.q_values(obs[e], taus=None if taus is None else taus[e], noise=noise).cpu().numpy()
+    np.testing.assert_allclose(q[e], q1, rtol=2e-6, atol=1e-6)
+    want = min(int(u[1, e] * A), A - 1) if u[0, e] < eps else int(np.argmax(q[e]))
+    assert actions[e] == want, (e, actions[e], want)
+  greedy, _ = L.act_batch(obs, taus=taus, noise=noise)
+  assert np.array_equal(greedy.cpu().numpy(), np.argmax(q, axis=1))
+
+
+def test_batched_actor_runs_many_streams_with_one_copy_per_tick():
+  from dqn_zoo_b200 import agent as agent_lib
+  from dqn_zoo_b200 import learner as dl
+  from oracle import learner_oracle as lo
+  L = dl.Learner(dl.NetworkSpec('dqn', 6), batch_size=32)
+  L.set_params(lo.init_params(lo.NetSpec('dqn', 6), 2), also_target=True)
+  actor = agent_lib.BatchedEpsilonGreedyActor(L, 32, exploration_epsilon=0.05, rng_key=[0, 9])
+  obs = torch.randint(0, 256, (32, 84, 84, 4), dtype=torch.uint8, device='cuda')
+  a = actor.step(obs)
+  assert a.shape == (32,) and a.dtype == np.int32 and a.min() >= 0 and a.max() < 6
+  q = actor.q_values.cpu().numpy()
+  agree = (a == np.argmax(q, axis=1)).mean()
+  assert agree > 0.8   # epsilon = 0.05
