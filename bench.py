@@ -131,15 +131,15 @@ def host_cores():
 
 def reference_arm(args, rank, world):
   """The oracle PORT of the reference algorithm on the host cores (rank 0 only; the other ranks exit without work).
-  torchrun exports OMP_NUM_THREADS=1, so the thread count is set explicitly to every core this process may use, and
-  reported.  Ten untimed pre-warm steps (thread pools, allocator) come before the W warm-up + K timed steps."""
+  torchrun exports OMP_NUM_THREADS=1, so the thread count is set explicitly: calibrated over {4, 8, ..., CPUs this process
+  may use} (the batch-32 learner is 3-4x slower on 64 OpenMP threads than on 8) and reported.  Ten untimed pre-warm steps
+  (thread pools, allocator) come before the W warm-up + K timed steps."""
   if rank != 0:
     return
   from oracle import cpu_reference
-  cores = host_cores()
   steps, warmup = max(1, args.steps), max(0, args.warmup)
   res = cpu_reference.run(args.agent, capacity=args.capacity, batch=args.batch, steps=steps, warmup=warmup, seed=args.seed,
-                          threads=cores, prewarm=10, budget_s=150.0)
+                          threads='auto', prewarm=10, budget_s=100.0)
   value = res['steps_per_s']
   sample = ('%d learner steps (replay.sample + update + update_priorities) of %s after %d warm-up (+10 pre-warm) steps; replay '
             '%.2f ms + learner %.2f ms per step; observations reference a pool of 512 synthetic frames'
@@ -460,7 +460,7 @@ def main():
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
     from oracle import cpu_reference
     res = cpu_reference.run(args.agent, capacity=args.capacity, batch=B, steps=args.cpu_steps, warmup=2, seed=args.seed,
-                            budget_s=25.0)
+                            threads='auto', budget_s=25.0)
     cpu = {'value': res['steps_per_s'], 'unit': 'grad-steps/s', 'cores': res['cores'], 'kind': 'port',
            'sample': '%d learner steps of the same workload: numpy replay %.2f ms + torch-CPU f32 learner %.2f ms per step'
                      % (res['steps'], res['replay_ms'], res['learner_ms'])}

@@ -108,9 +108,6 @@ _SIGNATURES = {
     'dz_learner_act_batch': (i32, [vp, vp, i32, vp, vp, vp, f32, vp, vp, vp]),
     'dz_learner_sync_target': (i32, [vp, vp]),
     'dz_test_u8_to_unit': (i32, [vp, vp]),
-    'dz_test_tc_set_variant': (i32, [i32]),
-    'dz_test_tc_gemm': (i32, [vp, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp, i32, i32, i32, i64, i64, i32, i64,
-                              i32, vp]),
     'dz_atari_preprocess': (i32, [vp, vp, i32, vp, vp, vp, vp, i32, vp, i32, vp]),
     'dz_atari_preprocess_band_rows': (i32, []),
     'dz_jax_uniform': (i32, [vp, vp, i32, vp, vp]),

@@ -22,8 +22,6 @@ int launch_sample(const dz_replay_view* view, int prioritized, const dz_sample_i
 int launch_update_priorities(const dz_replay_view* view, const int64_t* d_indices, const float* d_priorities, int n,
                              double alpha, int64_t size, void* stream);
 
-struct TcBatch;
-int launch_tc(const char* tag, const TcBatch& tb, int bnj, void* stream);
 
 // ---- packed-operand tcgen05 GEMM (dz_tcp.cuh / dz_tcp.cu) ------------------------------------------------------
 constexpr int kPkKB = 16;         // reduction elements per k-block / pipeline stage

@@ -15,6 +15,7 @@
 #include <map>
 #include <vector>
 
+#include "dz_gemm.cuh"
 #include "dz_tc.cuh"
 #include "dz_internal.cuh"
 #include "dz_umma_net.cuh"
@@ -917,11 +918,19 @@ __device__ __forceinline__ float opt_one(const OptArgs& o, float p, float g, flo
   if (KIND == DZ_ADAM) {  // optax.scale_by_adam: eps outside the sqrt, bias-corrected moments
     float mu = o.b1 * m + (1.0f - o.b1) * g;
     float nu = o.b2 * v + (1.0f - o.b2) * g * g;
+    // Moments of parameters whose gradient stays zero decay THROUGH the denormal range (0.9^t reaches 1e-38 after ~800
+    // steps) and every warp that holds one takes the slow paths of the IEEE division / square root below: measured, the
+    // optimizer launch went 42.7 -> 58.5 us between step 50 and step 4000 of a run.  A denormal moment cannot change a
+    // parameter (|update| < 1e-38 / eps), so it is stored as zero.
+    if (fabsf(mu) < 1.17549435e-38f) mu = 0.f;
+    if (nu < 1.17549435e-38f) nu = 0.f;
     m = mu; v = nu;
     upd = (mu * inv_c1) / (sqrtf(nu * inv_c2) + o.eps);
   } else {                // optax.rmsprop(centered=True): eps inside the sqrt
     float mu = o.decay * m + (1.0f - o.decay) * g;
     float nu = o.decay * v + (1.0f - o.decay) * g * g;
+    if (fabsf(mu) < 1.17549435e-38f) mu = 0.f;   // see the Adam branch: no denormal moments in memory
+    if (nu < 1.17549435e-38f) nu = 0.f;
     m = mu; v = nu;
     upd = g * (1.0f / sqrtf(nu - mu * mu + o.eps));
   }
@@ -1283,184 +1292,16 @@ int launch_batch(const char* tag, KernelT kernel, const GemmBatch& gb, dim3 grid
 #define DZ_TRY(expr) do { int _s = (expr); if (_s != DZ_OK) return _s; } while (0)
 
 
-// ---- tcgen05 path: the same grouped problems, re-expressed as D[i,j] = sum_r A(i,r) B(j,r) ----------------
-
-// Which grouped GEMMs run on the tcgen05 kernel (dz_tc.cuh) instead of the fp32-FMA kernels (dz_gemm.cuh).
-// Round-1 status: the tcgen05 path is parity-green for every layer of the dqn/c51/qr/rainbow family but its
-// register-path loaders still cost more issue slots than the FMA kernels' whole inner loop at these tile
-// counts (profiles/r01_tc_vs_simt.md), so it is opt-in: DZ_TC=all, or DZ_TC=<tag>,<tag>,... per layer tag.
-bool g_use_tc = false;
-std::string g_tc_layers;
-
 void read_env() {
-  g_use_tc = getenv("DZ_TC") != nullptr && std::string(getenv("DZ_TC")) != "0";
-  g_tc_layers = getenv("DZ_TC") ? getenv("DZ_TC") : "";
   g_pk_iqn = !(getenv("DZ_PK_IQN") != nullptr && std::string(getenv("DZ_PK_IQN")) == "0");
   g_fc_splits = getenv("DZ_FC_SPLITS") ? atoi(getenv("DZ_FC_SPLITS")) : 0;
   g_conv1_splits = getenv("DZ_CONV1_SPLITS") ? atoi(getenv("DZ_CONV1_SPLITS")) : 1;
   g_umma = !(getenv("DZ_UMMA") != nullptr && std::string(getenv("DZ_UMMA")) == "0");
 }
 
-bool tc_enabled_for(const char* tag) {
-  if (!g_use_tc) return false;
-  if (g_tc_layers.empty() || g_tc_layers == "all") return true;
-  std::string t = std::string(",") + tag + ",";
-  return (std::string(",") + g_tc_layers + ",").find(t) != std::string::npos;
-}
-
-TcOperand tc_plain(const float* ptr, int na, int nb, int ld, int red_is_b, const float* scale_r = nullptr) {
-  TcOperand o;
-  memset(&o, 0, sizeof(o));
-  o.ptr = ptr; o.a_mode = A_PLAIN; o.na = na; o.nb = nb; o.ld = ld; o.red_is_b = red_is_b; o.scale_r = scale_r; o.ones_row = -1;
-  return o;
-}
-// The (possibly implicit-im2col) A matrix of a GemmProblem as a source S[a = m][b = k].
-TcOperand tc_from_A(const GemmProblem& p, int red_is_b, const float* scale_r = nullptr) {
-  TcOperand o;
-  memset(&o, 0, sizeof(o));
-  o.ptr = p.A; o.a_mode = p.a_mode; o.na = p.M; o.nb = p.K; o.ld = p.lda;
-  o.H = p.H; o.W = p.W; o.Cin = p.Cin; o.S = p.S; o.OH = p.OH; o.OW = p.OW; o.seg = p.seg;
-  o.red_is_b = red_is_b; o.scale_r = scale_r; o.ones_row = -1;
-  return o;
-}
-
-bool tc_a_ok(const GemmProblem& p) {
-  if (p.K % 4) return false;
-  if (p.a_mode == A_PLAIN) return (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
-  return true;
-}
-
-// NN: C[M,N] = A[M,K] B[K,N].  Problems must be in partial mode (splits > 1) or plain bias/ReLU epilogues.
-int run_nn_tc(const char* tag, const GemmBatch& gb, bool dual, void* stream, bool* handled) {
-  *handled = false;
-  if (!tc_enabled_for(tag) || dual) return DZ_OK;   // noisy (dual) layers: effective-weight FMA kernels
-  int maxM = 0, maxN = 0;
-  for (int i = 0; i < gb.n; ++i) {
-    const GemmProblem& p = gb.p[i];
-    if (!tc_a_ok(p) || p.mul || p.C2 || (p.bias_shared && p.splits <= 1)) return DZ_OK;
-    if (dual && p.splits <= 1) return DZ_OK;
-    if ((reinterpret_cast<uintptr_t>(p.B) & 15) || (dual && (reinterpret_cast<uintptr_t>(p.B2) & 15))) return DZ_OK;
-    maxM = std::max(maxM, p.M); maxN = std::max(maxN, p.N);
-  }
-  if (gb.n * (dual ? 2 : 1) > kTcMaxProblems) return DZ_OK;
-  TcBatch tb;
-  memset(&tb, 0, sizeof(tb));
-  const bool swap = maxM <= 64;        // skinny batch: the weights become the 128-row MMA operand
-  for (int i = 0; i < gb.n; ++i) {
-    const GemmProblem& p = gb.p[i];
-    for (int d = 0; d < (dual ? 2 : 1); ++d) {
-      TcProblem t;
-      memset(&t, 0, sizeof(t));
-      t.redirect_row = -1;
-      const float* W = d == 0 ? p.B : p.B2;
-      const float* xs = d == 0 ? nullptr : p.a_scale;          // sigma term: x is scaled by eps_in along k
-      TcOperand act = tc_from_A(p, 1, xs);                     // S[m][k], contiguous along the reduction
-      TcOperand wgt = tc_plain(W, p.K, p.N, p.ldb, 0);         // S[k][n], contiguous along the rows (transposed on load)
-      long long half = (long long)p.M * p.ldc;                 // sigma partial follows the mu partial
-      t.R = p.K;
-      t.splits = p.splits;
-      t.split_stride = p.splits > 1 ? p.split_stride : 0;
-      t.C = p.C + (d ? half : 0);
-      if (!swap && p.a_mode == A_CONV_U8) {                    // conv1: raw bytes are exact TF32 numbers; 1/255 rides on the weights
-        act.exact = 1; act.u8_raw = 1;
-        wgt.mul_all = 0.0039215688593685627f;
-      }
-      if (swap) { t.A = wgt; t.B = act; t.MI = p.N; t.NJ = p.M; t.sc_i = 1; t.sc_j = p.ldc; }
-      else      { t.A = act; t.B = wgt; t.MI = p.M; t.NJ = p.N; t.sc_i = p.ldc; t.sc_j = 1; }
-      if (p.splits <= 1) {                                     // direct epilogue
-        if (swap) return DZ_OK;                                // (bias is indexed by i there; not needed today)
-        t.bias_j = p.bias; t.relu = p.relu;
-      }
-      tb.p[tb.n++] = t;
-    }
-  }
-  int bnj = swap ? (maxM <= 32 ? 32 : 64) : (maxN <= 32 ? 32 : (maxN <= 64 ? 64 : 128));
-  *handled = true;
-  return launch_tc(tag, tb, bnj, stream);
-}
-
-// TN: C[K(+1),N] = A[M,K]^T G[M,N]; always written as raw partials [Kext][N] (split_stride > 0).
-int run_tn_tc(const char* tag, const GemmBatch& gb, void* stream, bool* handled) {
-  *handled = false;
-  if (!tc_enabled_for(tag) || gb.n > kTcMaxProblems) return DZ_OK;
-  int maxN = 0;
-  for (int i = 0; i < gb.n; ++i) {
-    const GemmProblem& p = gb.p[i];
-    if (!tc_a_ok(p)) return DZ_OK;
-    if ((reinterpret_cast<uintptr_t>(p.B) & 15) || p.ldb % 4) return DZ_OK;
-    maxN = std::max(maxN, p.N);
-  }
-  TcBatch tb;
-  memset(&tb, 0, sizeof(tb));
-  for (int i = 0; i < gb.n; ++i) {
-    const GemmProblem& p = gb.p[i];
-    const int kext = p.K + ((p.Cb || p.Cb2) ? 1 : 0);
-    TcProblem t;
-    memset(&t, 0, sizeof(t));
-    t.redirect_row = -1;
-    t.A = tc_from_A(p, 0);                                     // S[m][k]: tile rows = k, reduction = m
-    t.A.ones_row = kext > p.K ? p.K : -1;                      // bias-gradient row
-    if (p.a_mode == A_CONV_U8) {                               // conv1 wgrad: exact byte operand, 1/255 applied to the output
-      t.A.exact = 1; t.A.u8_raw = 1; t.A.ones_value = 255.0f;
-      t.out_scale = 0.0039215688593685627f;
-    }
-    t.B = tc_plain(p.B, p.M, p.N, p.ldb, 0);                   // G[m][n]: tile rows = n, reduction = m
-    t.MI = kext; t.NJ = p.N; t.R = p.M;
-    if (p.split_stride > 0) {            // raw partials [Kext][N]
-      t.C = p.C; t.sc_i = p.N; t.sc_j = 1; t.splits = p.splits; t.split_stride = p.split_stride;
-    } else {                             // direct: weight grads (+ sigma grads) and bias row(s)
-      t.C = p.C; t.sc_i = p.ldc; t.sc_j = 1; t.splits = 1; t.split_stride = 0;
-      t.C2 = p.C2; t.s2_i = p.a_scale; t.s2_j = p.c_scale;
-      t.redirect_row = kext > p.K ? p.K : -1; t.Cb = p.Cb; t.Cb2 = p.Cb2;
-    }
-    tb.p[tb.n++] = t;
-  }
-  *handled = true;
-  return launch_tc(tag, tb, maxN <= 32 ? 32 : (maxN <= 64 ? 64 : 128), stream);
-}
-
-// NT: C[M,K] = G[M,N] W[K,N]^T (+ dual): raw store (splits == 1, no mask) or raw partials [M][K].
-int run_nt_tc(const char* tag, const GemmBatch& gb, bool dual, void* stream, bool* handled) {
-  *handled = false;
-  if (!tc_enabled_for(tag) || dual || gb.n > kTcMaxProblems) return DZ_OK;
-  int maxM = 0, maxK = 0;
-  for (int i = 0; i < gb.n; ++i) {
-    const GemmProblem& p = gb.p[i];
-    if (p.lda % 4 || p.ldb % 4 || p.N % 4) return DZ_OK;
-    if ((reinterpret_cast<uintptr_t>(p.A) & 15) || (reinterpret_cast<uintptr_t>(p.B) & 15)) return DZ_OK;
-    if (p.splits <= 1 && (p.mask || dual)) return DZ_OK;
-    maxM = std::max(maxM, p.M); maxK = std::max(maxK, p.K);
-  }
-  const bool swap = maxM <= 64;
-  TcBatch tb;
-  memset(&tb, 0, sizeof(tb));
-  for (int i = 0; i < gb.n; ++i) {
-    const GemmProblem& p = gb.p[i];
-    for (int d = 0; d < (dual ? 2 : 1); ++d) {
-      TcProblem t;
-      memset(&t, 0, sizeof(t));
-      t.redirect_row = -1;
-      TcOperand g = tc_plain(static_cast<const float*>(p.A), p.M, p.N, p.lda, 1, d ? p.c_scale : nullptr);  // G[m][n], scaled by eps_out along n
-      TcOperand w = tc_plain(d ? p.B2 : p.B, p.K, p.N, p.ldb, 1);                                           // W[k][n]
-      long long out_ld = p.splits > 1 ? p.K : p.ldc;
-      t.R = p.N; t.splits = p.splits; t.split_stride = p.splits > 1 ? p.split_stride : 0;
-      t.C = p.C + (d ? (long long)p.M * p.K : 0);
-      if (swap) { t.A = w; t.B = g; t.MI = p.K; t.NJ = p.M; t.sc_i = 1; t.sc_j = out_ld; }
-      else      { t.A = g; t.B = w; t.MI = p.M; t.NJ = p.K; t.sc_i = out_ld; t.sc_j = 1; }
-      tb.p[tb.n++] = t;
-    }
-  }
-  int bnj = swap ? (maxM <= 32 ? 32 : 64) : (maxK <= 32 ? 32 : (maxK <= 64 ? 64 : 128));
-  *handled = true;
-  return launch_tc(tag, tb, bnj, stream);
-}
-
 // ---- NN launch helpers (tile shapes chosen by M / N) -------------------------------------------
 
 int run_nn(const char* tag, GemmBatch& gb, bool dual, void* stream) {
-  bool handled = false;
-  DZ_TRY(run_nn_tc(tag, gb, dual, stream, &handled));
-  if (handled) return DZ_OK;
   int maxM = 0, maxN = 0, maxS = 1;
   for (int i = 0; i < gb.n; ++i) {
     maxM = gb.p[i].M > maxM ? gb.p[i].M : maxM;
@@ -1482,9 +1323,6 @@ int run_nn(const char* tag, GemmBatch& gb, bool dual, void* stream) {
 }
 
 int run_tn(const char* tag, GemmBatch& gb, void* stream) {
-  bool handled = false;
-  DZ_TRY(run_tn_tc(tag, gb, stream, &handled));
-  if (handled) return DZ_OK;
   int maxK = 0, maxN = 0, maxS = 1;
   for (int i = 0; i < gb.n; ++i) {
     int kext = gb.p[i].K + ((gb.p[i].Cb || gb.p[i].Cb2) ? 1 : 0);
@@ -1501,9 +1339,6 @@ int run_tn(const char* tag, GemmBatch& gb, void* stream) {
 }
 
 int run_nt(const char* tag, GemmBatch& gb, bool dual, void* stream) {
-  bool handled = false;
-  DZ_TRY(run_nt_tc(tag, gb, dual, stream, &handled));
-  if (handled) return DZ_OK;
   int maxM = 0, maxK = 0, maxS = 1;
   for (int i = 0; i < gb.n; ++i) {
     maxM = gb.p[i].M > maxM ? gb.p[i].M : maxM;
@@ -2597,6 +2432,19 @@ int dz_learner_act_batch(dz_learner* l, const uint8_t* d_obs, int32_t E, const f
   size_t smem = (32 + c.num_atoms + 8) * sizeof(float);
   DZ_LAUNCH(q_values_kernel, (unsigned)E, 128, smem, stream, c.kind, c.num_actions, c.num_atoms, nq, c.vmax, l->out[1], l->out[1], l->outv[1], d_q_out);
   DZ_LAUNCH(act_select_kernel, (unsigned)ceil_div(E, 128), 128, 0, stream, (const float*)d_q_out, c.num_actions, (int)E, d_explore, epsilon, d_actions);
+  return DZ_OK;
+}
+
+namespace {
+__global__ void u8_to_unit_table_kernel(float* out) {
+  dz::pdl_enter();
+  out[threadIdx.x] = u8_to_unit(threadIdx.x);
+}
+}  // namespace
+
+// Test hook: the device's uint8 -> float32/255 conversion of 0..255 (the conv1 operand load of the fp32-FMA kernels).
+int dz_test_u8_to_unit(float* d_out256, void* stream) {
+  DZ_LAUNCH(u8_to_unit_table_kernel, 1, 256, 0, stream, d_out256);
   return DZ_OK;
 }
 

@@ -304,18 +304,6 @@ int dz_learner_sync_target(dz_learner* l, void* stream);
  * into d_out256 so tests can check it is the correctly rounded quotient. */
 int dz_test_u8_to_unit(float* d_out256, void* stream);
 
-/* Debug knob for the self-test below (descriptor variants while bringing the kernel up). */
-int dz_test_tc_set_variant(int32_t v);
-
-/* Self-test hook of the tcgen05 (3xTF32) GEMM used by the learner: D[i,j] = sum_r A(i,r)*B(j,r) over plain
- * row-major sources S[a][b] (leading dimension ld; red_is_b = 1: reduction runs along b (K-major operand),
- * 0: along a (MN-major operand)); optional per-r scales; raw partial sums of split s at
- * d_C + s*split_stride + i*sc_i + j*sc_j.  tile_n in {32, 64, 128}.  Used only by tests/. */
-int dz_test_tc_gemm(const float* d_A, int32_t a_na, int32_t a_nb, int32_t a_ld, int32_t a_red_is_b,
-                    const float* d_B, int32_t b_na, int32_t b_nb, int32_t b_ld, int32_t b_red_is_b,
-                    const float* d_scale_a, const float* d_scale_b, int32_t a_ones_row, float* d_C, int32_t MI,
-                    int32_t NJ, int32_t R, int64_t sc_i, int64_t sc_j, int32_t splits, int64_t split_stride,
-                    int32_t tile_n, void* stream);
 
 /* Self-test of the packed-operand tcgen05 GEMM (csrc/dz_tcp.cuh; the IQN 3136->512 layer's kernels): packs
  * A (a_rows x red) and B (b_rows x red) from plain fp32 matrices (x_red_contig = 1: element (row, r) at
