@@ -258,6 +258,7 @@ def main():
   d_draws = torch.as_tensor(draws, device=device)
   for i in range(W):
     ag.learn_from_device_draws(d_draws[i])
+  sync_target()   # warm-up of the refresh path too (the first NCCL broadcast pays communicator set-up: 1.6 ms measured at N = 2)
   barrier()
   launches_before = _lib.lib.dz_launch_count()
   clocks = ClockSampler(local_rank)
