@@ -299,6 +299,157 @@ class BatchedAtariPreprocessor:
               C.cast(self._luma, C.c_void_p), self._max_band_rows, torch.cuda.current_stream().cuda_stream)
 
 
+class VectorScalars:
+  """The scalar half of `processors.atari()` for n streams as numpy array code (no per-stream Python objects): exactly the
+  state machine of `BatchedAtariPreprocessor.step()` — ZeroDiscountOnLifeLoss (processors.py:254-260), FixedPaddedBuffer
+  (:121-163), TimestepBufferCondition (:165-215), none_to_zero_pad + reduce_step_type + reward/discount aggregation
+  (:54-66, 267-365, 464-481) — with `None` rewards / discounts carried as masks.  Pure host code: tested on CPU against the
+  per-stream implementation and the oracle (tests/test_oracle_processors.py)."""
+
+  FIRST, MID, LAST = int(StepType.FIRST), int(StepType.MID), int(StepType.LAST)
+
+  def __init__(self, n, repeats, gamma, clip, life_loss, stack):
+    self.n, self.R, self.gamma, self.clip, self.life_loss, self.stack = n, repeats, gamma, clip, life_loss, stack
+    self.reset()
+
+  def reset(self, streams=None):
+    n, R = self.n, self.R
+    if streams is None:
+      self.lives = np.zeros(n, np.int64); self.has_lives = np.zeros(n, bool)
+      self.index = np.full(n, (-1) % R, np.int64)
+      self.valid = np.zeros((n, R), bool); self.type = np.zeros((n, R), np.int64)
+      self.reward = np.zeros((n, R)); self.reward_none = np.zeros((n, R), bool)
+      self.disc = np.zeros((n, R)); self.disc_none = np.zeros((n, R), bool)
+      self.has_frame = np.zeros((n, R), bool)
+      self.since = np.zeros(n, np.int64); self.since_none = np.ones(n, bool)
+      self.should_reset = np.zeros(n, bool)
+      self.count = np.zeros(n, np.int64)
+      return
+    e = np.asarray(streams)
+    self.has_lives[e] = False; self.index[e] = (-1) % R
+    self.valid[e] = False; self.has_frame[e] = False
+    self.since_none[e] = True; self.should_reset[e] = False; self.count[e] = 0
+
+  def tick(self, step_type, reward, discount, lives, active=None):
+    """One raw timestep per active stream.  reward / discount: float64 arrays, NaN = None.  Returns a dict:
+    emit (bool [n]), pooled_slot (int [n]; >= 0: this tick's frame goes to that pooled slot), and for emitting streams
+    step_type, reward, discount (NaN = None), a_ok / b_ok (pooled frames present), count (stack fill before the push)."""
+    n, R = self.n, self.R
+    act = np.ones(n, bool) if active is None else np.asarray(active, bool)
+    st = np.asarray(step_type, np.int64)
+    rw = np.asarray(reward, np.float64).copy(); rn = np.isnan(rw)
+    dc = np.asarray(discount, np.float64).copy(); dn = np.isnan(dc)
+    lv = np.asarray(lives, np.int64)
+    if self.life_loss:
+      lost = act & (st == self.MID) & self.has_lives & (lv < self.lives)
+      self.lives = np.where(act, lv, self.lives); self.has_lives |= act
+      dc[lost] = 0.0; dn[lost] = False
+    wrap = act & (self.index >= R)
+    self.index[wrap] = 0; self.valid[wrap] = False; self.has_frame[wrap] = False
+    rows = np.nonzero(act)[0]; col = self.index[rows]
+    self.valid[rows, col] = True; self.type[rows, col] = st[rows]
+    self.reward[rows, col] = np.where(rn[rows], 0.0, rw[rows]); self.reward_none[rows, col] = rn[rows]
+    self.disc[rows, col] = np.where(dn[rows], 0.0, dc[rows]); self.disc_none[rows, col] = dn[rows]
+    pooled = np.where(act, self.index - (R - 2), -1)
+    up = rows[pooled[rows] >= 0]
+    self.has_frame[up, self.index[up]] = True
+    self.index[rows] += 1
+    # ---- TimestepBufferCondition
+    if np.any(act & self.should_reset):
+      raise RuntimeError('Should have reset.')
+    boundary = self.valid & ((self.type == self.FIRST) | (self.type == self.LAST))
+    nb = boundary.sum(axis=1)
+    if np.any(act & (nb > 1)):
+      raise RuntimeError('Expected at most one FIRST or LAST.')
+    main = np.where(nb == 1, (self.type * boundary).sum(axis=1), self.MID)   # FIRST = 0: a lone FIRST sums to 0
+    is_first = act & (nb == 1) & (boundary & (self.type == self.FIRST)).any(axis=1)
+    is_last = act & (nb == 1) & ~is_first
+    del main
+    if np.any(act & self.since_none & ~is_first):
+      raise RuntimeError('After reset first timestep should be FIRST.')
+    mid = act & ~is_first & ~is_last
+    self.since[is_first] = 0; self.since_none[is_first] = False
+    self.since_none[is_last] = True; self.should_reset[is_last] = True
+    self.since[mid] += 1
+    emit = is_first | is_last | (mid & (self.since % R == 0))
+    # ---- reduce (none_to_zero_pad: padding slots count as type 0 = FIRST, reward 0.0, discount 0.0)
+    t = np.where(self.valid, self.type, 0)
+    if np.any(emit[:, None] & ~np.isin(t, (self.FIRST, self.MID, self.LAST))):
+      raise ValueError('Expected MID if not FIRST or LAST.')
+    edge = (t == 0) | (t == self.LAST)
+    first_edge = np.argmax(edge, axis=1)
+    out_type = np.where(edge.any(axis=1), t[np.arange(n), first_edge], self.MID)
+    r_none = (self.valid & self.reward_none).any(axis=1)
+    r = np.zeros(n)
+    for j in range(R):
+      r = r + np.where(self.valid[:, j], self.reward[:, j], 0.0)       # python's sum(): left to right from 0
+    if self.clip:
+      r = np.maximum(np.minimum(r, self.clip), -self.clip)
+    d_none = (self.valid & self.disc_none).any(axis=1)
+    d = np.ones(n)
+    for j in range(R):
+      d = d * np.where(self.valid[:, j], self.disc[:, j], 0.0)
+    d = self.gamma * d
+    a_ok = self.has_frame[:, R - 2] & self.valid[:, R - 2]
+    b_ok = self.has_frame[:, R - 1] & self.valid[:, R - 1]
+    count = self.count.copy()
+    self.count = np.where(emit, np.minimum(self.count + 1, self.stack), self.count)
+    return {'emit': emit, 'pooled_slot': pooled, 'step_type': out_type, 'reward': np.where(r_none, np.nan, r),
+            'discount': np.where(d_none, np.nan, d), 'a_ok': a_ok, 'b_ok': b_ok, 'count': count}
+
+
+class VectorizedAtariPreprocessor(BatchedAtariPreprocessor):
+  """`processors.atari()` for many environment streams whose raw frames are ALREADY on the device (a GPU emulator, or one
+  staged H2D copy of all streams' frames per tick): `step_arrays()` takes struct-of-arrays timesteps, runs the scalar state
+  machine as numpy array code (`VectorScalars`; no per-stream Python objects) and the pixel kernel once per tick.  Emits
+  arrays, not TimeStep objects; the frame stacks stay in `self.stacks` for `Learner.act_batch` / the replay insert."""
+
+  def __init__(self, num_streams: int = 1, **kwargs):
+    super().__init__(num_streams=num_streams, **kwargs)
+    self._vs = VectorScalars(num_streams, self._repeats, self._gamma, self._clip, self._life_loss, self._stack)
+    self._all = torch.arange(num_streams)
+
+  def reset(self, stream: Optional[int] = None) -> None:
+    self._vs.reset(None if stream is None else [stream])
+    if self._in_shape is not None:
+      (self._stacks if stream is None else self._stacks[stream]).zero_()
+
+  def step_arrays(self, frames, step_type, reward, discount, lives, active=None):
+    """frames: uint8 [n, H, W, 3] (device tensor, or a host array -> one H2D copy); step_type int [n]; reward / discount
+    float [n] with NaN for None (FIRST timesteps); lives int [n].  Returns VectorScalars.tick()'s dict (host arrays)."""
+    if self._in_shape is None:
+      self._allocate(tuple(frames.shape[1:]))
+    frames = torch.as_tensor(frames, device=self._device)
+    out = self._vs.tick(step_type, reward, discount, lives, active)
+    for slot in (0, 1):
+      e = np.nonzero(out['pooled_slot'] == slot)[0]
+      if e.size == self._n:
+        self._raw[:, slot].copy_(frames, non_blocking=True)
+      elif e.size:
+        idx = torch.as_tensor(e, device=self._device)
+        self._raw[:, slot].index_copy_(0, idx, frames.index_select(0, idx))
+    emit = np.nonzero(out['emit'])[0]
+    if emit.size:
+      k = emit.size
+      if self._meta_pending:
+        self._meta_done.synchronize()
+      raw0, stride_e = self._raw.data_ptr(), self._raw.stride(0)
+      slot_bytes = self._raw.stride(1)
+      meta = self._meta_host.numpy()
+      meta[0, :k] = np.where(out['a_ok'][emit], raw0 + emit * stride_e, 0)
+      meta[1, :k] = np.where(out['b_ok'][emit], raw0 + emit * stride_e + slot_bytes, 0)
+      meta[2, :k] = self._stacks.data_ptr() + emit * self._stacks.stride(0)
+      meta[3, :k] = out['count'][emit]
+      self._meta.copy_(self._meta_host, non_blocking=True)
+      self._meta_done.record()
+      self._meta_pending = True
+      self._counts[:k].copy_(self._meta[3, :k])
+      _lib.call('dz_atari_preprocess', self._meta[0].data_ptr(), self._meta[1].data_ptr(), int(k), C.byref(self._axis_h.c),
+                C.byref(self._axis_v.c), self._meta[2].data_ptr(), self._counts.data_ptr(), self._stack,
+                C.cast(self._luma, C.c_void_p), self._max_band_rows, torch.cuda.current_stream().cuda_stream)
+    return out
+
+
 class _SingleStream:
   """The reference's per-environment processor object: `__call__(timestep)` and `reset()`."""
 

@@ -111,6 +111,41 @@ def test_many_streams_in_one_launch():
   assert dev.stacks.shape == (n, 84, 84, 4) and dev.stacks.is_cuda
 
 
+def test_vectorized_device_frame_path_equals_the_per_stream_path():
+  """VectorizedAtariPreprocessor.step_arrays (device-resident frames, array state machine, one launch per tick) against
+  BatchedAtariPreprocessor.step (host frames, per-stream objects) on the same desynchronised episodes: identical
+  emissions and bit-identical frame stacks after every tick."""
+  from dqn_zoo_b200 import processors
+  rs = np.random.RandomState(21)
+  n = 6
+  a = processors.BatchedAtariPreprocessor(num_streams=n, device_observations=True)
+  b = processors.VectorizedAtariPreprocessor(num_streams=n, device_observations=True)
+  episodes = [random_episode(rs, 11 + 3 * e, (210, 160, 3), life_loss_at=(5 if e % 2 else None)) for e in range(n)]
+  blank = np.zeros((210, 160, 3), np.uint8)
+  for t in range(max(len(ep) for ep in episodes)):
+    batch, act = [], np.zeros(n, bool)
+    frames = np.zeros((n, 210, 160, 3), np.uint8)
+    st_a = np.ones(n, np.int64); rw = np.zeros(n); dc = np.ones(n); lv = np.zeros(n, np.int64)
+    for e in range(n):
+      if t < len(episodes[e]):
+        st, r, d, f, lives = episodes[e][t]
+        batch.append(ts(st, r, d, f, lives))
+        act[e] = True; frames[e] = f; st_a[e] = int(st); lv[e] = lives
+        rw[e] = np.nan if r is None else r; dc[e] = np.nan if d is None else d
+      else:
+        batch.append(None); frames[e] = blank
+    outs = a.step(batch)
+    got = b.step_arrays(torch.as_tensor(frames, device='cuda'), st_a, rw, dc, lv, act)
+    torch.cuda.synchronize()
+    for e in range(n):
+      assert (outs[e] is not None) == bool(got['emit'][e]), (t, e)
+      if outs[e] is not None:
+        assert int(outs[e].step_type) == int(got['step_type'][e])
+        assert (outs[e].reward is None and np.isnan(got['reward'][e])) or outs[e].reward == got['reward'][e]
+        assert (outs[e].discount is None and np.isnan(got['discount'][e])) or outs[e].discount == got['discount'][e]
+    assert torch.equal(a.stacks, b.stacks), t
+
+
 def test_saturated_and_black_frames():
   from dqn_zoo_b200 import processors
   for value in (0, 255):

@@ -244,3 +244,69 @@ def test_first_has_no_reward_or_discount_and_last_is_reported():
     feed(1, 1.0, 1.0)
     out = feed(2, 1.0, 0.0)
     assert out[0] == po.LAST and out[2] == 0.0 and out[1] == 1.0   # 3 summed, clipped to 1
+
+
+def test_vectorized_scalar_state_machine_equals_the_per_stream_one():
+  """VectorScalars (numpy array code over n streams) against the per-stream host state machine of
+  BatchedAtariPreprocessor.step() on desynchronised random episodes: FIRST/LAST boundaries, idle ticks, life losses,
+  resets after LAST, None rewards/discounts of FIRST timesteps — every emission identical (type, reward, discount, which
+  pooled frames exist, stack fill)."""
+  from dqn_zoo_b200 import processors as dev
+  n, R = 9, 4
+  rs = np.random.RandomState(4)
+  product = dev.BatchedAtariPreprocessor(num_streams=n, resize_shape=(4, 4), additional_discount=0.99, max_abs_reward=1.0)
+  vs = dev.VectorScalars(n, R, 0.99, 1.0, True, 4)
+  FIRST, MID, LAST = int(dev.StepType.FIRST), int(dev.StepType.MID), int(dev.StepType.LAST)
+  need_first = np.ones(n, bool)
+  lives = np.full(n, 3)
+  emissions = 0
+  for tick in range(600):
+    active = rs.uniform(size=n) < 0.85
+    st = np.full(n, MID); rw = np.zeros(n); dc = np.ones(n)
+    for e in range(n):
+      if not active[e]:
+        continue
+      if need_first[e]:
+        st[e], rw[e], dc[e], lives[e] = FIRST, np.nan, np.nan, 3
+        need_first[e] = False
+      else:
+        st[e] = LAST if rs.uniform() < 0.03 else MID
+        rw[e] = float(rs.choice([0.0, 1.0, -1.0, 2.5, -3.0]))
+        dc[e] = 0.0 if st[e] == LAST else 1.0
+        if rs.uniform() < 0.05 and lives[e] > 0:
+          lives[e] -= 1
+    out = vs.tick(st, rw, dc, lives, active)
+    for e in range(n):
+      if not active[e]:
+        assert not out['emit'][e]
+        continue
+      s = product._streams[e]
+      r = None if np.isnan(rw[e]) else float(rw[e])
+      d = None if np.isnan(dc[e]) else float(dc[e])
+      if product._life_loss:
+        lost = st[e] == MID and lives[e] < s.lives
+        s.lives = int(lives[e])
+        if lost:
+          d = 0.0
+      if s.index >= R:
+        s.index = 0; s.slots = [None] * R; s.has_frame = [False] * R
+      s.slots[s.index] = (dev.StepType(int(st[e])), r, d)
+      if s.index - (R - 2) >= 0:
+        s.has_frame[s.index] = True
+      assert out['pooled_slot'][e] == s.index - (R - 2) if s.index - (R - 2) >= 0 else out['pooled_slot'][e] < 0
+      s.index += 1
+      emit = product._should_emit(s)
+      assert bool(out['emit'][e]) == emit, (tick, e)
+      if emit:
+        emissions += 1
+        t, rr, dd = product._reduce_scalars(s)
+        assert int(t) == int(out['step_type'][e])
+        assert (rr is None and np.isnan(out['reward'][e])) or rr == out['reward'][e]
+        assert (dd is None and np.isnan(out['discount'][e])) or dd == out['discount'][e]
+        assert bool(out['a_ok'][e]) == (s.has_frame[R - 2] and s.slots[R - 2] is not None)
+        assert bool(out['b_ok'][e]) == (s.has_frame[R - 1] and s.slots[R - 1] is not None)
+        assert int(out['count'][e]) == s.count
+        s.count = min(s.count + 1, 4)
+        if int(t) == LAST:                    # the run loop resets the processor after a LAST timestep
+          s.reset(); vs.reset([e]); need_first[e] = True
+  assert emissions > 800
