@@ -233,10 +233,13 @@ __global__ void __launch_bounds__(256) finish_tn_kernel(const __grid_constant__ 
 struct FinishNT {  // split partials [M][K] (+ dual second half) of up to two NT problems -> summed, masked output
   const float* partial[2]; const float* a_scale[2]; int nsrc; int splits; long long stride; int M, K; int dual;
   const float* mask; float* out;
+  float* out_hi; float* out_lo;   // optional: the tf32 hi/lo pair the tcgen05 kernels read (saves a separate split launch)
 };
+struct FinishNTBatch { FinishNT f[2]; };   // blockIdx.y selects the job
 
-__global__ void __launch_bounds__(256) finish_nt_kernel(FinishNT f) {
+__global__ void __launch_bounds__(256) finish_nt_kernel(const __grid_constant__ FinishNTBatch fb) {
   dz::pdl_enter();
+  const FinishNT& f = fb.f[blockIdx.y];
   long long total = (long long)f.M * f.K;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     float v = 0.f;
@@ -247,6 +250,11 @@ __global__ void __launch_bounds__(256) finish_nt_kernel(FinishNT f) {
     }
     if (f.mask && !(f.mask[i] > 0.f)) v = 0.f;
     f.out[i] = v;
+    if (f.out_hi) {
+      const float h = tc::rn_tf32(v);
+      f.out_hi[i] = h;
+      f.out_lo[i] = tc::rn_tf32(v - h);
+    }
   }
 }
 
@@ -1684,15 +1692,27 @@ int forward_heads_iqn(dz_learner* l, const Pass* passes, int np, int nimg, const
 
 // ---- backward ----------------------------------------------------------------------------------
 
-int finish_nt(const GemmProblem* probs, int nsrc, const float* mask, float* out, bool dual, void* stream) {
+FinishNT make_finish_nt(const GemmProblem* probs, int nsrc, const float* mask, float* out, bool dual, float* out_hi = nullptr,
+                        float* out_lo = nullptr) {
   FinishNT f;
   memset(&f, 0, sizeof(f));
   f.nsrc = nsrc; f.splits = probs[0].splits; f.stride = probs[0].split_stride; f.M = probs[0].M; f.K = probs[0].K;
-  f.dual = dual ? 1 : 0; f.mask = mask; f.out = out;
+  f.dual = dual ? 1 : 0; f.mask = mask; f.out = out; f.out_hi = out_hi; f.out_lo = out_lo;
   for (int q = 0; q < nsrc; ++q) { f.partial[q] = probs[q].C; f.a_scale[q] = probs[q].a_scale; }
-  long long total = (long long)f.M * f.K;
-  DZ_LAUNCH(finish_nt_kernel, (unsigned)std::min<long long>(ceil_div(total, 256), 148 * 8), 256, 0, stream, f);
+  return f;
+}
+int finish_nt_batch(const FinishNT* jobs, int njobs, void* stream) {
+  FinishNTBatch fb;
+  memset(&fb, 0, sizeof(fb));
+  long long total = 0;
+  for (int j = 0; j < njobs; ++j) { fb.f[j] = jobs[j]; total = std::max(total, (long long)jobs[j].M * jobs[j].K); }
+  dim3 grid((unsigned)std::min<long long>(ceil_div(total, 256), 148 * 8), (unsigned)njobs);
+  DZ_LAUNCH(finish_nt_kernel, grid, 256, 0, stream, fb);
   return DZ_OK;
+}
+int finish_nt(const GemmProblem* probs, int nsrc, const float* mask, float* out, bool dual, void* stream) {
+  FinishNT f = make_finish_nt(probs, nsrc, mask, out, dual);
+  return finish_nt_batch(&f, 1, stream);
 }
 
 // Returns the side stream after making it wait for everything enqueued on `stream` so far (or `stream`
@@ -1906,7 +1926,13 @@ int backward_rainbow(dz_learner* l, const float* noise, void* stream) {
     gb.p[s] = p;
   }
   DZ_TRY(run_nt("noisy2_dgrad", gb, true, stream));
-  for (int s = 0; s < 2; ++s) DZ_TRY(finish_nt(&gb.p[s], 1, l->h1[0][s], l->dh1[s], true, stream));
+  {   // both streams' dh1 in one launch; on the tcgen05 path it also writes the tf32 hi/lo pair noisy1_dgrad reads
+    FinishNT jobs[2];
+    for (int s = 0; s < 2; ++s)
+      jobs[s] = make_finish_nt(&gb.p[s], 1, l->h1[0][s], l->dh1[s], true, l->um ? um_dh1_hi(l->um, s) : nullptr,
+                               l->um ? um_dh1_lo(l->um, s) : nullptr);
+    DZ_TRY(finish_nt_batch(jobs, 2, stream));
+  }
   for (int s = 0; s < 2; ++s) {  // first noisy layer weight grads
     std::string pre = std::string(st[s]) + "1/";
     GemmProblem p = zero_problem();
@@ -1918,8 +1944,7 @@ int backward_rainbow(dz_learner* l, const float* noise, void* stream) {
   }
   DZ_TRY(run_tn("noisy1_wgrad", gb, fork_side(l, stream)));
   if (l->um) {
-    DZ_TRY(um_split_dh1(l->um, stream));
-    DZ_TRY(um_backward_fc(l->um, noise, stream));
+    DZ_TRY(um_backward_fc(l->um, noise, stream));   // dh1 hi/lo came from the finish kernel above
     return DZ_OK;
   }
   for (int s = 0; s < 2; ++s) {  // dact3 contributions

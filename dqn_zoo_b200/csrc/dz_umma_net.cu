@@ -1404,6 +1404,8 @@ float* um_act_f32(UmNet* n, int layer, int pass) {
 float* um_dact_f32(UmNet* n, int layer) { return n->dact_f32[layer - 1]; }
 float* um_h1_f32(UmNet* n, int pass, int stream) { return n->h1_buf + ((int64_t)pass * n->d.nstream + stream) * n->d.B * 512; }
 float* um_dh1_f32(UmNet* n, int stream) { return n->dh1_f32 + (int64_t)stream * n->d.B * 512; }
+float* um_dh1_hi(UmNet* n, int stream) { return n->dh1_hi + (int64_t)stream * n->d.B * 512; }
+float* um_dh1_lo(UmNet* n, int stream) { return n->dh1_lo + (int64_t)stream * n->d.B * 512; }
 
 int um_pack_weights(UmNet* n, void* stream) {
   PackArgs a;

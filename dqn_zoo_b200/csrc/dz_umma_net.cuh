@@ -37,6 +37,8 @@ float* um_act_f32(UmNet* n, int layer, int pass);      // layer 1..3 -> [B][h][w
 float* um_dact_f32(UmNet* n, int layer);               // layer 1..3: d loss / d (pre-ReLU masked) activation of pass 0
 float* um_h1_f32(UmNet* n, int pass, int stream);      // [B][512] (post-ReLU)
 float* um_dh1_f32(UmNet* n, int stream);               // [B][512] gradient wrt h1 (already masked), INPUT of um_backward_fc
+float* um_dh1_hi(UmNet* n, int stream);               // tf32 hi / lo of dh1 (written by the producer or by um_split_dh1)
+float* um_dh1_lo(UmNet* n, int stream);
 
 // One launch each unless noted.  rows[p]: row-pointer table of pass p (uint8 observations, gathered in place).
 int um_pack_weights(UmNet* n, void* stream);                                   // conv weight images (both nets)
