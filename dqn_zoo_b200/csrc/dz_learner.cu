@@ -1860,12 +1860,27 @@ int backward_plain(dz_learner* l, void* stream) {
     DZ_TRY(run_tn("head_wgrad", gb, fork_side(l, stream)));
     if (shared) DZ_LAUNCH(sum_to_scalar_kernel, 1, 128, 0, (l->side && l->side_dirty ? (void*)l->side : stream), l->scalars + 8 + kNormBlocks, d.out, G + L.off("head/b"));
   }
+  bool dh1_split_done = false;
   {  // dh1 = dout * Wh^T, masked by h1 > 0
     GemmProblem p = zero_problem();
     p.A = l->dout; p.lda = d.out; p.M = B; p.N = d.out; p.K = 512;
     p.B = P + L.off("head/w"); p.ldb = d.out; p.C = l->dh1[0]; p.ldc = 512; p.mask = l->h1[0][0];
-    gb.p[0] = p;
-    DZ_TRY(run_nt("head_dgrad", gb, false, stream));
+    // Wide heads (c51: 306 outputs, qr-dqn: 1206): with one CTA column per 64 outputs of dh1 the reduction over the head
+    // width is a serial chain (measured 24 / 65 us); split it and let the finish kernel apply the mask (and, on the tcgen05
+    // path, write the tf32 hi/lo pair fc1_dgrad reads, which saves the separate split launch).
+    const int splits = d.out > 64 ? (int)std::min<int64_t>(16, ceil_div(d.out, 96)) : 1;
+    if (splits > 1) {
+      p.splits = splits; p.split_stride = (long long)B * 512; p.C = l->nt_partial; p.mask = nullptr;
+      gb.p[0] = p;
+      DZ_TRY(run_nt("head_dgrad", gb, false, stream));
+      FinishNT job = make_finish_nt(&gb.p[0], 1, l->h1[0][0], l->dh1[0], false, l->um ? um_dh1_hi(l->um, 0) : nullptr,
+                                    l->um ? um_dh1_lo(l->um, 0) : nullptr);
+      DZ_TRY(finish_nt_batch(&job, 1, stream));
+      dh1_split_done = l->um != nullptr;
+    } else {
+      gb.p[0] = p;
+      DZ_TRY(run_nt("head_dgrad", gb, false, stream));
+    }
   }
   {  // fc1 wgrad
     GemmProblem p = zero_problem();
@@ -1876,7 +1891,7 @@ int backward_plain(dz_learner* l, void* stream) {
     DZ_TRY(run_tn("fc1_wgrad", gb, fork_side(l, stream)));
   }
   if (l->um) {   // dact3 on the tcgen05 path: dh1 -> tf32 hi/lo, W streamed once through TMA, split partials + masked finish
-    DZ_TRY(um_split_dh1(l->um, stream));
+    if (!dh1_split_done) DZ_TRY(um_split_dh1(l->um, stream));
     DZ_TRY(um_backward_fc(l->um, nullptr, stream));
   } else {  // dact3 = dh1 * Wf^T, masked by act3 > 0
     GemmProblem p = zero_problem();

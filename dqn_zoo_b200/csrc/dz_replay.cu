@@ -336,10 +336,14 @@ __global__ void __launch_bounds__(1024) per_sample_kernel(dz_replay_view v, dz_s
     double prob = __dadd_rn(__dmul_rn(__dsub_rn(1.0, usp), frac), __dmul_rn(usp, one_over_n));
     if (lane == 0) {
       int64_t id = v.d_id_at[idx];
+      const int64_t slot = id % v.capacity;
       out.d_indices[q] = idx;
       out.d_ids[q] = id;
-      out.d_slots[q] = id % v.capacity;
+      out.d_slots[q] = slot;
       out.d_probs[q] = prob;
+      // row pointers and scalars of the sampled transition do not depend on the batch-wide weight normalisation: their
+      // (DRAM-latency) loads are issued here, under the pow() and the block reduction, instead of after them
+      emit_batch_rows(v, ex, q, slot, 0.0);
       s_w[q] = is_weight_pow(__ddiv_rn(one_over_n, prob), beta);
     }
   }
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(1024) per_sample_kernel(dz_replay_view v, dz_s
     if (!(w <= 1.7976931348623157e308 && w >= -1.7976931348623157e308) && v.d_flags)
       atomicOr(v.d_flags, DZ_FLAG_NONFINITE_WEIGHT);
     out.d_weights[q] = w;
-    emit_batch_rows(v, ex, q, out.d_slots[q], w);
+    if (ex.d_w) ex.d_w[q] = (float)w;
   }
 }
 
