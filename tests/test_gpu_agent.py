@@ -331,3 +331,38 @@ def test_batched_actor_runs_many_streams_with_one_copy_per_tick():
   q = actor.q_values.cpu().numpy()
   agree = (a == np.argmax(q, axis=1)).mean()
   assert agree > 0.8   # epsilon = 0.05
+
+
+def test_debug_timeline_stamps_every_kernel_of_a_graph_replayed_step():
+  """dz_debug_timeline: every kernel appends (globaltimer, launch geometry) after its griddepcontrol.wait, also under CUDA
+  graph replay — the instrument behind tools/step_timeline.py and bench.py's roofline timing.  One stamp per launch
+  (kernels with several (0,0,z) blocks stamp once per z), monotone within a step, and nothing is written once removed."""
+  from dqn_zoo_b200 import _lib
+  from dqn_zoo_b200 import replay as dr
+  rep = dr.TransitionReplay(512, dr.Transition(None, None, None, None, None), np.random.RandomState(4))
+  dr.bulk_fill_synthetic(rep, OBS, 4, 6)
+  ag = _make_agent('dqn', rep, 4, True)
+  for _ in range(4):
+    ag.learn()
+  torch.cuda.synchronize()
+  ag._use_graph = False
+  c0 = _lib.lib.dz_launch_count()
+  ag.learn()
+  torch.cuda.synchronize()
+  launches = int(_lib.lib.dz_launch_count() - c0)
+  ag._use_graph = True
+  tl = torch.zeros(2 + 2 * 4000, dtype=torch.int64, device='cuda')
+  _lib.call('dz_debug_timeline', tl.data_ptr())
+  steps = 5
+  for _ in range(steps):
+    ag.learn()
+  torch.cuda.synchronize()
+  _lib.call('dz_debug_timeline', 0)
+  t = tl.cpu().numpy()
+  n = int(t[0] & 0xffffffff)
+  assert n >= launches * steps and n % steps == 0, (n, launches, steps)
+  ts = np.sort(t[2:2 + 2 * n:2])
+  assert np.all(np.diff(ts) >= 0) and ts[-1] - ts[0] < 50_000_000     # < 50 ms for five steps
+  ag.learn()
+  torch.cuda.synchronize()
+  assert int(tl.cpu().numpy()[0] & 0xffffffff) == n
