@@ -701,6 +701,158 @@ __global__ void __launch_bounds__(128) loss_categorical_kernel(LossArgs L) {
   }
 }
 
+// Same kernel with the example's head outputs staged in shared memory first (identical arithmetic, identical results):
+// the default whenever 3 * A * atoms floats fit (they do for every standard configuration).
+__global__ void __launch_bounds__(128) loss_categorical_staged_kernel(LossArgs L) {
+  dz::pdl_enter();
+  extern __shared__ float sm[];
+  const int b = blockIdx.x, K = L.atoms, A = L.A, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* cm_sel = sm;            // [K] mean over actions of the selector-pass advantages (rainbow)
+  float* cm_tgt = cm_sel + K;    // [K] same for the target pass
+  float* cm_tm1 = cm_tgt + K;    // [K] same for the online(s_tm1) pass
+  float* p_tgt = cm_tm1 + K;     // [K]
+  float* proj = p_tgt + K;       // [K]
+  float* p_tm1 = proj + K;       // [K] softmax(logits_tm1[a_tm1])
+  float* qsel = p_tm1 + K;       // [A]
+  float* scal = qsel + A;        // [4]: loss, sum(proj)
+  float* zs = scal + 4;          // [K] support atoms
+  float* st_adv = zs + K;        // [3][A*K] head outputs of this example for pass 0 / 1 / 2
+  float* st_val = st_adv + 3 * A * K;   // [3][K] value-stream outputs (rainbow)
+  const bool rb = L.kind == DZ_RAINBOW;
+  // Everything this example's loss reads from the three head passes goes to shared memory in ONE round of coalesced,
+  // independent loads; the phases below are then shared-memory arithmetic instead of ~10 dependent global round trips.
+  {
+    const float* __restrict__ a0 = (rb ? L.adv0 : L.out0) + (long long)b * A * K;
+    const float* __restrict__ a1 = (rb ? L.adv1 : L.out2) + (long long)b * A * K;
+    const float* __restrict__ a2 = (rb ? L.adv2 : L.out2) + (long long)b * A * K;
+    for (int i = tid; i < A * K; i += blockDim.x) {
+      const float x0 = a0[i], x1 = a1[i], x2 = a2[i];
+      st_adv[i] = x0; st_adv[A * K + i] = x1; st_adv[2 * A * K + i] = x2;
+    }
+    if (rb) {
+      const float* __restrict__ v0 = L.val0 + (long long)b * K;
+      const float* __restrict__ v1 = L.val1 + (long long)b * K;
+      const float* __restrict__ v2 = L.val2 + (long long)b * K;
+      for (int i = tid; i < K; i += blockDim.x) {
+        const float x0 = v0[i], x1 = v1[i], x2 = v2[i];
+        st_val[i] = x0; st_val[K + i] = x1; st_val[2 * K + i] = x2;
+      }
+    }
+    for (int i = tid; i < K; i += blockDim.x) zs[i] = (float)((double)(-L.vmax) + (double)i * (2.0 * (double)L.vmax / (double)(K - 1)));
+  }
+  __syncthreads();
+  auto support = [&](int i) { return zs[i]; };
+
+  // 0. dueling column means (networks.py:251: mean over the action axis)
+  if (rb) {
+    for (int k = tid; k < K; k += blockDim.x) {
+      float m1 = 0.f, m2 = 0.f, m0 = 0.f;
+      for (int a = 0; a < A; ++a) {
+        m1 += st_adv[A * K + a * K + k];
+        m2 += st_adv[2 * A * K + a * K + k];
+        m0 += st_adv[a * K + k];
+      }
+      cm_sel[k] = m1 / (float)A; cm_tgt[k] = m2 / (float)A; cm_tm1[k] = m0 / (float)A;
+    }
+  }
+  __syncthreads();
+  // logit k of (pass, action): pass 0 = online(s_tm1), 1 = selector, 2 = target
+  auto logit_of = [&](int pass, int a, int k) -> float {
+    if (rb) {
+      const float* cm = pass == 0 ? cm_tm1 : (pass == 1 ? cm_sel : cm_tgt);
+      return st_val[pass * K + k] + st_adv[pass * A * K + a * K + k] - cm[k];
+    }
+    return st_adv[(pass == 0 ? 0 : 2) * A * K + a * K + k];   // c51 selects with the target network
+  };
+  // warp-level softmax of (pass, a): returns this lane's max/denominator; optionally writes probabilities
+  auto warp_softmax = [&](int pass, int a, float* probs, float& mx, float& den) {
+    float m = -INFINITY;
+    for (int k = lane; k < K; k += 32) m = fmaxf(m, logit_of(pass, a, k));
+    mx = warp_max(m);
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) s += expf(logit_of(pass, a, k) - mx);
+    den = warp_sum(s);
+    if (probs)
+      for (int k = lane; k < K; k += 32) probs[k] = expf(logit_of(pass, a, k) - mx) / den;
+  };
+
+  // 1. selector q-values, one warp per action
+  for (int a = warp; a < A; a += 4) {
+    float mx, den;
+    warp_softmax(rb ? 1 : 2, a, nullptr, mx, den);
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) s += (expf(logit_of(rb ? 1 : 2, a, k) - mx) / den) * support(k);
+    s = warp_sum(s);
+    if (lane == 0) qsel[a] = s;
+  }
+  __syncthreads();
+  int best = 0;
+  for (int a = 1; a < A; ++a)
+    if (qsel[a] > qsel[best]) best = a;
+  const int at = L.a[b];
+  // 2. target distribution (warp 0) and softmax of the taken action's online logits (warp 1)
+  float mx_tm1 = 0.f, den_tm1 = 1.f;
+  if (warp == 0) { float mx, den; warp_softmax(2, best, p_tgt, mx, den); }
+  if (warp == 1) {
+    warp_softmax(0, at, p_tm1, mx_tm1, den_tm1);
+    if (lane == 0) { scal[2] = mx_tm1; scal[3] = den_tm1; }
+  }
+  __syncthreads();
+  // 3. rlax.categorical_l2_project(r + discount*z, p, z)
+  const float r = L.r[b], dsc = L.disc[b];
+  const float zmin = support(0), zmax = support(K - 1);
+  for (int i = tid; i < K; i += blockDim.x) {
+    float zi = support(i);
+    float dpos = (i + 1 < K ? support(i + 1) : support(0)) - zi;      // roll(z,-1) - z
+    float dneg = zi - (i > 0 ? support(i - 1) : support(K - 1));      // z - roll(z,1)
+    dpos = dpos > 0.f ? 1.0f / dpos : 0.f;
+    dneg = dneg > 0.f ? 1.0f / dneg : 0.f;
+    float acc = 0.f;
+    for (int j = 0; j < K; ++j) {
+      float zp = fminf(fmaxf(r + dsc * support(j), zmin), zmax);
+      float delta = zp - zi;
+      float dhat = delta >= 0.f ? delta * dpos : -(delta * dneg);
+      acc += fminf(fmaxf(1.0f - dhat, 0.f), 1.0f) * p_tgt[j];
+    }
+    proj[i] = acc;
+  }
+  __syncthreads();
+  // 4. cross entropy with log_softmax(logits_tm1[a_tm1]) (warp 0)
+  if (warp == 0) {
+    const float mx = scal[2], logden = logf(scal[3]);
+    float ls = 0.f, ps = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      ls += proj[k] * (logit_of(0, at, k) - mx - logden);
+      ps += proj[k];
+    }
+    ls = warp_sum(ls); ps = warp_sum(ps);
+    if (lane == 0) { scal[0] = -ls; scal[1] = ps; }
+  }
+  __syncthreads();
+  const float loss = scal[0], psum = scal[1];
+  const float w = L.w ? L.w[b] : 1.0f;
+  const float cot = w / (float)L.B;
+  // 5. gradient wrt the pass-0 head outputs
+  if (rb) {
+    for (int k = tid; k < K; k += blockDim.x) {
+      float dl = cot * (p_tm1[k] * psum - proj[k]);
+      L.dval[(long long)b * K + k] = dl;
+      for (int a = 0; a < A; ++a)
+        L.dadv[((long long)b * A + a) * K + k] = dl * ((a == at ? 1.0f : 0.0f) - 1.0f / (float)A);
+    }
+  } else {
+    for (int i = tid; i < A * K; i += blockDim.x) {
+      int a = i / K, k = i - a * K;
+      L.dout[(long long)b * A * K + i] = (a == at) ? cot * (p_tm1[k] * psum - proj[k]) : 0.f;
+    }
+  }
+  if (tid == 0) {
+    L.per_example[b] = loss;
+    if (L.priorities) L.priorities[b] = fminf(fmaxf(fabsf(loss), 0.f), 100.f);  // rainbow/agent.py:194
+    L.loss_terms[b] = w * loss;
+  }
+}
+
 // qrdqn / iqn: rlax.quantile_q_learning with quantile_regression_loss (Huber kappa).
 // Layouts: qrdqn out[b, q*A + a] (networks.py:308), iqn out[(b*N + n)*A + a] (networks.py:286-287).
 __global__ void __launch_bounds__(256) loss_quantile_kernel(LossArgs L) {
@@ -2215,16 +2367,20 @@ int update_impl(dz_learner* l, const dz_batch* batch, const dz_update_outputs* o
     DZ_LAUNCH(loss_q_kernel, B, 64, 0, stream, L);
   } else if (c.kind == DZ_C51 || c.kind == DZ_RAINBOW) {
     size_t smem = (6 * c.num_atoms + c.num_actions + 4) * sizeof(float);
-    DZ_LAUNCH(loss_categorical_kernel, B, 128, smem, stream, L);
+    const size_t staged = (size_t)(c.num_atoms + 3 * c.num_actions * c.num_atoms + 3 * c.num_atoms) * sizeof(float);
+    if (smem + staged <= 40 * 1024) DZ_LAUNCH_NAMED("loss_categorical_kernel", loss_categorical_staged_kernel, B, 128, smem + staged, stream, L);
+    else DZ_LAUNCH(loss_categorical_kernel, B, 128, smem, stream, L);
   } else {
     if (c.kind == DZ_QRDQN) { L.N = c.num_quantiles; L.Ksel = c.num_quantiles; L.Nt = c.num_quantiles; }
     else { L.N = c.tau_samples_s_tm1; L.Ksel = c.tau_samples_policy; L.Nt = c.tau_samples_s_t; }
     size_t smem = (32 + c.num_actions + L.Nt + 2 * L.N) * sizeof(float);
     DZ_LAUNCH(loss_quantile_kernel, B, 256, smem, stream, L);
   }
-  DZ_LAUNCH(loss_mean_kernel, 1, 32, 0, stream, l->loss_terms, B, out->d_loss, max_seen, L.priorities);
-  if (wb) {   // replay.update_priorities(ids, priorities) (rainbow/agent.py:198): independent of the backward pass
-    DZ_TRY(launch_update_priorities(wb->view, wb->indices, wb->priorities, B, wb->alpha, wb->view->capacity, fork_side(l, stream)));
+  {   // the scalar loss / running max priority and replay.update_priorities(ids, priorities) (rainbow/agent.py:198) are
+      // independent of the backward pass: both leave the critical path for the side stream
+    void* ls = fork_side(l, stream);
+    DZ_LAUNCH(loss_mean_kernel, 1, 32, 0, ls, l->loss_terms, B, out->d_loss, max_seen, L.priorities);
+    if (wb) DZ_TRY(launch_update_priorities(wb->view, wb->indices, wb->priorities, B, wb->alpha, wb->view->capacity, ls));
   }
 
   // ---- backward through online(s_tm1)
