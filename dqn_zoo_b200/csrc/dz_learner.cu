@@ -1044,15 +1044,18 @@ struct OptArgs {
   float* p; const float* g; float* m; float* v; long long n; const float* norm; const int64_t* counters;
   // split global norm (tcgen05 path): norm = sqrt(fc_sumsq[0] + sum of parts[0..nparts)), recomputed identically by every block
   const float* parts; int nparts; const float* fc_sumsq; float* norm_out; float* user_norm;
+  int stages;   // optimizer_bulk_kernel: depth of the shared-memory ring
 };
 
 // Fixed-order block reduction of the split-norm partials: every block of every launch gets the same bits.
 __device__ __forceinline__ float split_norm(const float* __restrict__ parts, int nparts, const float* __restrict__ fc_sumsq) {
   __shared__ float s_red[8];
   float t = 0.f;
-  for (int i = threadIdx.x; i < nparts; i += 256) t += __ldcg(parts + i);
-  t = warp_sum(t);
-  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = t;
+  if (threadIdx.x < 256) {   // the first 256 threads reduce (blocks of 256 or 512 threads): one fixed order
+    for (int i = threadIdx.x; i < nparts; i += 256) t += __ldcg(parts + i);
+    t = warp_sum(t);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = t;
+  }
   __syncthreads();
   float tot = __ldcg(fc_sumsq);
 #pragma unroll
@@ -1155,6 +1158,122 @@ __global__ void __launch_bounds__(256) optimizer_kernel(OptArgs o) {
       }
     }
   }
+}
+
+// The same update as a bulk-copy (TMA 1-D) pipeline: the four streams of a 256-quadruple chunk land in shared memory by
+// cp.async.bulk (one elected thread, mbarrier complete_tx), 256 threads update them in place, and p / m / v leave by
+// cp.async.bulk stores.  Memory-level parallelism no longer depends on registers x resident warps: every CTA keeps
+// `stages` - 1 chunks (16 KB each) of loads in flight while it computes, and the LSU sees shared-memory traffic only.
+// Identical arithmetic (opt_one), identical results.
+constexpr int kOptStagesMax = 8;
+constexpr int kOptChunk = 256;                            // float4 per stream per stage = one per thread
+constexpr int kOptStageBytes = 4 * kOptChunk * 16;        // p, g, m, v
+
+__device__ __forceinline__ void opt_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(dst)),
+               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(tc::smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void opt_bulk_store(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(dst)),
+               "r"(tc::smem_u32(src)), "r"(bytes)
+               : "memory");
+}
+
+template <int KIND, int V>   // V floats per thread and stage: 4 (256 threads) or 2 (512 threads, twice the warps per byte of shared memory)
+__global__ void __launch_bounds__(kOptChunk * 4 / V, V == 2 ? 4 : 1) optimizer_bulk_kernel(OptArgs o) {
+  extern __shared__ __align__(128) unsigned char opt_sm[];
+  const int kOptStages = o.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(opt_sm + kOptStages * kOptStageBytes);
+  const int tid = threadIdx.x;
+  const long long n4 = o.n >> 2;
+  const long long nchunks = (n4 + kOptChunk - 1) / kOptChunk;
+  const long long mine = blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;   // chunks of this CTA
+  float4* p4 = reinterpret_cast<float4*>(o.p);
+  const float4* g4 = reinterpret_cast<const float4*>(o.g);
+  float4* m4 = reinterpret_cast<float4*>(o.m);
+  float4* v4 = reinterpret_cast<float4*>(o.v);
+  if (tid == 0) {
+    for (int s = 0; s < kOptStages; ++s) tc::mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  dz::pdl_enter();
+  auto issue = [&](long long it, int s) {   // thread 0: loads of this CTA's it-th chunk into stage s = it % stages
+    const long long c = blockIdx.x + it * gridDim.x;
+    const long long q0 = c * kOptChunk;
+    const uint32_t bytes = (uint32_t)(min((long long)kOptChunk, n4 - q0) * 16);
+    unsigned char* st = opt_sm + s * kOptStageBytes;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(&full[s])), "r"(4 * bytes) : "memory");
+    opt_bulk_load(st, p4 + q0, bytes, &full[s]);
+    opt_bulk_load(st + kOptChunk * 16, g4 + q0, bytes, &full[s]);
+    opt_bulk_load(st + 2 * kOptChunk * 16, m4 + q0, bytes, &full[s]);
+    opt_bulk_load(st + 3 * kOptChunk * 16, v4 + q0, bytes, &full[s]);
+  };
+  // the first loads are issued BEFORE the norm is formed (see optimizer_kernel)
+  if (tid == 0)
+    for (long long it = 0; it < mine && it < kOptStages; ++it) issue(it, (int)it);
+  float norm;
+  if (o.parts != nullptr) {
+    norm = split_norm(o.parts, o.nparts, o.fc_sumsq);
+    if (blockIdx.x == 0 && tid == 0) { o.norm_out[0] = norm; if (o.user_norm) o.user_norm[0] = norm; }
+  } else {
+    norm = o.norm[0];
+  }
+  const bool clip = o.max_norm > 0.f && !(norm < o.max_norm);  // optax.clip_by_global_norm trigger
+  float c1 = 1.f, c2 = 1.f;
+  if (KIND == DZ_ADAM) {
+    float t = (float)o.counters[0];
+    c1 = 1.0f / (1.0f - powf(o.b1, t));
+    c2 = 1.0f / (1.0f - powf(o.b2, t));
+  }
+  int s = 0;
+  uint32_t phase = 0;
+  for (long long it = 0; it < mine; ++it) {
+    const long long q0 = (blockIdx.x + it * gridDim.x) * (long long)kOptChunk;
+    const int valid = (int)min((long long)kOptChunk, n4 - q0);
+    float4* sp = reinterpret_cast<float4*>(opt_sm + s * kOptStageBytes);
+    float4* sg = sp + kOptChunk;
+    float4* smm = sp + 2 * kOptChunk;
+    float4* sv = sp + 3 * kOptChunk;
+    if (tid == 0 && it > 0) {   // refill the stage of iteration it - 1 as soon as its stores have finished READING it
+      const long long next = it - 1 + kOptStages;
+      if (next < mine) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        issue(next, s == 0 ? kOptStages - 1 : s - 1);
+      }
+    }
+    tc::mbar_wait(&full[s], phase);
+    if (V == 4) {
+      if (tid < valid) {
+        float4 p = sp[tid], g = sg[tid], m = smm[tid], v = sv[tid];
+        p.x = opt_one<KIND>(o, p.x, g.x, m.x, v.x, clip, norm, c1, c2);
+        p.y = opt_one<KIND>(o, p.y, g.y, m.y, v.y, clip, norm, c1, c2);
+        p.z = opt_one<KIND>(o, p.z, g.z, m.z, v.z, clip, norm, c1, c2);
+        p.w = opt_one<KIND>(o, p.w, g.w, m.w, v.w, clip, norm, c1, c2);
+        sp[tid] = p; smm[tid] = m; sv[tid] = v;
+      }
+    } else {
+      if (tid < 2 * valid) {
+        float2 p = reinterpret_cast<float2*>(sp)[tid], g = reinterpret_cast<float2*>(sg)[tid];
+        float2 m = reinterpret_cast<float2*>(smm)[tid], v = reinterpret_cast<float2*>(sv)[tid];
+        p.x = opt_one<KIND>(o, p.x, g.x, m.x, v.x, clip, norm, c1, c2);
+        p.y = opt_one<KIND>(o, p.y, g.y, m.y, v.y, clip, norm, c1, c2);
+        reinterpret_cast<float2*>(sp)[tid] = p; reinterpret_cast<float2*>(smm)[tid] = m; reinterpret_cast<float2*>(sv)[tid] = v;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk stores
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)valid * 16;
+      opt_bulk_store(p4 + q0, sp, bytes);
+      opt_bulk_store(m4 + q0, smm, bytes);
+      opt_bulk_store(v4 + q0, sv, bytes);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    if (++s == kOptStages) { s = 0; phase ^= 1u; }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the grid does
 }
 
 // epsilon-greedy over q[E][A] (dqn/agent.py:121-127): first maximum wins, as np.argmax / jnp.argmax.
@@ -2287,6 +2406,34 @@ int run_optimizer(dz_learner* l, float* user_norm, bool apply, void* stream) {
             l->buf.d_online, l->buf.d_grads, l->buf.d_opt_state, l->buf.d_opt_state + n, n, norm, l->buf.d_counters,
             parts, nparts, l->scalars + 1, norm, user_norm};
   static const int per_sm = getenv("DZ_OPT_BLOCKS") ? atoi(getenv("DZ_OPT_BLOCKS")) : 8;
+  // DZ_OPT_BULK=0: the register-staged kernel (A/B measurements)
+  static const bool bulk = !(getenv("DZ_OPT_BULK") && getenv("DZ_OPT_BULK")[0] == '0');
+  if (bulk) {
+    static const int bulk_per_sm = getenv("DZ_OPT_BLOCKS") ? atoi(getenv("DZ_OPT_BLOCKS")) : 4;
+    static const int stages = std::min(kOptStagesMax, std::max(2, getenv("DZ_OPT_STAGES") ? atoi(getenv("DZ_OPT_STAGES")) : 3));
+    const int kOptSmem = stages * kOptStageBytes + 64;
+    o.stages = stages;
+    static const int vec = (getenv("DZ_OPT_VEC") && atoi(getenv("DZ_OPT_VEC")) == 4) ? 4 : 2;
+    static bool attr_done = false;
+    if (!attr_done) {
+      DZ_CUDA_OK(cudaFuncSetAttribute(optimizer_bulk_kernel<DZ_ADAM, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOptSmem));
+      DZ_CUDA_OK(cudaFuncSetAttribute(optimizer_bulk_kernel<DZ_RMSPROP_CENTERED, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOptSmem));
+      DZ_CUDA_OK(cudaFuncSetAttribute(optimizer_bulk_kernel<DZ_ADAM, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOptSmem));
+      DZ_CUDA_OK(cudaFuncSetAttribute(optimizer_bulk_kernel<DZ_RMSPROP_CENTERED, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOptSmem));
+      attr_done = true;
+    }
+    const long long nchunks = ((o.n >> 2) + kOptChunk - 1) / kOptChunk;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(148LL * bulk_per_sm, nchunks));
+    const unsigned threads = kOptChunk * 4 / vec;
+    if (c.optimizer == DZ_ADAM) {
+      if (vec == 4) DZ_LAUNCH_NAMED("optimizer_kernel", (optimizer_bulk_kernel<DZ_ADAM, 4>), grid, threads, kOptSmem, stream, o);
+      else DZ_LAUNCH_NAMED("optimizer_kernel", (optimizer_bulk_kernel<DZ_ADAM, 2>), grid, threads, kOptSmem, stream, o);
+    } else {
+      if (vec == 4) DZ_LAUNCH_NAMED("optimizer_kernel", (optimizer_bulk_kernel<DZ_RMSPROP_CENTERED, 4>), grid, threads, kOptSmem, stream, o);
+      else DZ_LAUNCH_NAMED("optimizer_kernel", (optimizer_bulk_kernel<DZ_RMSPROP_CENTERED, 2>), grid, threads, kOptSmem, stream, o);
+    }
+    return DZ_OK;
+  }
   if (c.optimizer == DZ_ADAM) DZ_LAUNCH_NAMED("optimizer_kernel", optimizer_kernel<DZ_ADAM>, 148 * per_sm, 256, 0, stream, o);
   else DZ_LAUNCH_NAMED("optimizer_kernel", optimizer_kernel<DZ_RMSPROP_CENTERED>, 148 * per_sm, 256, 0, stream, o);
   return DZ_OK;
