@@ -185,3 +185,32 @@ def test_codec_pair_is_validated_on_the_host():
   import pytest
   with pytest.raises(ValueError):
     replay._check_codec(lambda t: t, None)
+
+
+def test_cpu_reference_arm_thread_calibration():
+  """The `--impl reference` arm calibrates its OpenMP thread count (64 threads were 3-4x slower than 8-16 on the GPU box's
+  host): pick_threads keeps the fastest candidate within the CPUs the process may use and leaves torch set to it."""
+  import time
+  import torch
+  from oracle import cpu_reference as cr
+  limit = cr.cgroup_cpu_limit()
+  assert isinstance(limit, int) and limit >= 1
+
+  class FakeLearner:
+    calls = []
+
+    def update(self, *inputs):
+      t = torch.get_num_threads()
+      self.calls.append(t)
+      time.sleep(0.002 if t == 8 else 0.02)   # 8 threads is the optimum of this fake
+
+  before = torch.get_num_threads()
+  try:
+    fake = FakeLearner()
+    best = cr.pick_threads(fake, lambda: (), 64)
+    assert best == 8 and torch.get_num_threads() == 8
+    assert set(fake.calls) <= {4, 8, 16, 32, 64}
+    # a limit below the smallest candidate falls back to the limit itself
+    assert cr.pick_threads(FakeLearner(), lambda: (), 2) == 2
+  finally:
+    torch.set_num_threads(before)
